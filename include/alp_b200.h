@@ -1,0 +1,236 @@
+/*
+ * alp_b200.h — C ABI of the B200-native ALP / ALP_RD column codec.
+ *
+ * This is the drop-in boundary.  The reference (cwida/ALP) has no C ABI:
+ * it is a set of header-only C++ templates plus libALP.so with C++-mangled ffor/unffor/falp
+ * overloads.  Each entry point below names the reference primitive(s) it replaces
+ * (file:line relative to the reference tree).  `include/alp_b200.hpp` re-creates the
+ * reference's template signatures on top of this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - `d_` pointers are device memory, `h_` pointers are host memory
+ *   - every function returns 0 on success or a negative ALPB200_E* code; the message of the
+ *     last failure on the calling thread is available from alpb200_last_error()
+ *   - the library never allocates on the batched hot path: the caller owns all buffers
+ *   - vector = 1024 values, row-group = 100 vectors (reference include/alp/config.hpp:11-15)
+ */
+#ifndef ALP_B200_H
+#define ALP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALPB200_VECTOR_SIZE 1024u          /* config.hpp:11 VECTOR_SIZE */
+#define ALPB200_ROWGROUP_VECTORS 100u      /* config.hpp:13 N_VECTORS_PER_ROWGROUP */
+#define ALPB200_ROWGROUP_SIZE 102400u      /* config.hpp:15 ROWGROUP_SIZE */
+#define ALPB200_MAX_K 5                    /* config.hpp:22 MAX_K_COMBINATIONS */
+#define ALPB200_RD_DICT_SIZE 8             /* config.hpp:25 MAX_RD_DICTIONARY_SIZE */
+#define ALPB200_MAX_SAMPLES 288            /* 9 sampled vectors x 32 values (sampler.hpp:14-52) */
+
+/* alp::Scheme (constants.hpp:10-14) — same numeric values */
+#define ALPB200_SCHEME_INVALID 0
+#define ALPB200_SCHEME_ALP_RD 1
+#define ALPB200_SCHEME_ALP 2
+
+#define ALPB200_OK 0
+#define ALPB200_EINVAL (-1)   /* bad argument (null pointer, bw > lane width, misaligned buffer, ...) */
+#define ALPB200_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define ALPB200_ECAPACITY (-3)/* an output buffer of the column container is too small */
+#define ALPB200_ENODEVICE (-4)/* no CUDA device: there is no CPU fallback */
+
+/*
+ * Row-group state: the POD image of alp::state<PT> (encoder.hpp:35-62) that the encoder needs.
+ * Produced by alpb200_rowgroup_init_* (device) or by the caller (e.g. from the reference's own init).
+ */
+typedef struct alpb200_rg_state {
+	int32_t  scheme;                         /* ALPB200_SCHEME_* */
+	int32_t  k;                              /* state.k_combinations, 1..5 (ALP) */
+	uint8_t  combos[ALPB200_MAX_K][2];       /* state.best_k_combinations: {exponent, factor} */
+	uint8_t  right_bw;                       /* state.right_bit_width (ALP_RD) */
+	uint8_t  left_bw;                        /* state.left_bit_width  (ALP_RD) */
+	uint8_t  dict_size;                      /* state.actual_dictionary_size */
+	uint8_t  reserved0[3];
+	uint16_t dict[ALPB200_RD_DICT_SIZE];     /* state.left_parts_dict */
+	/* state.left_parts_dict_map entries that are NOT in the dictionary (rd.hpp:73-77): the index the
+	 * reference stores for such a left part before FFOR masks it to left_bw bits.  Only needed for byte
+	 * parity of the packed left stream at exception positions; n_extra = 0 is always valid
+	 * (then the stored index is dict_size, as rd.hpp:129-131 does for unseen keys). */
+	uint16_t n_extra;
+	uint16_t reserved1;
+	uint16_t extra_key[ALPB200_MAX_SAMPLES];
+	uint16_t extra_idx[ALPB200_MAX_SAMPLES];
+} alpb200_rg_state;
+
+/*
+ * Per-vector record of the column container (32 bytes, one 32-B sector per vector).
+ * It carries what the reference's callers keep per vector — bw, base, factor, exponent, exception
+ * count (test/test_alp_sample.cpp:6-7; publication/.../bench_end_to_end/include/encoding/helper.hpp:36-67
+ * `alp_m`) — plus the offsets of the vector's packed block and exception run.
+ */
+typedef struct alpb200_vec_meta {
+	union {
+		struct {
+			int64_t  base;                   /* FOR base (sign-extended for f32) — analyze_ffor, encoder.hpp:109-120 */
+			uint64_t reserved;
+		} alp;
+		uint16_t rd_dict[ALPB200_RD_DICT_SIZE]; /* ALP_RD: the row-group's left-part dictionary (rd.hpp:63-71) */
+	} u;
+	uint32_t packed_off;   /* offset of the packed block in `packed`, in units of 128 bytes.
+	                          ALP: 128*bw bytes.  ALP_RD: right block (128*bw bytes) then left block (128*e bytes) */
+	uint32_t exc_off;      /* first exception slot of this vector in exc_val / exc_pos */
+	uint16_t exc_cnt;      /* exceptions_count */
+	uint8_t  scheme;       /* ALPB200_SCHEME_ALP or ALPB200_SCHEME_ALP_RD */
+	uint8_t  bw;           /* ALP: FFOR bit width.  ALP_RD: right_bit_width */
+	uint8_t  e;            /* ALP: exponent index.  ALP_RD: left_bit_width */
+	uint8_t  f;            /* ALP: factor index.    ALP_RD: actual_dictionary_size */
+	uint8_t  reserved[2];
+} alpb200_vec_meta;
+
+/*
+ * Column container (struct of arrays; device pointers for the batched entry points, host pointers for
+ * the *_host entry points and for the CPU oracle).  Exceptions of all vectors are concatenated in vector
+ * order: exc_val[exc_off + i] / exc_pos[exc_off + i].  exc_val elements have the width of the column
+ * type (8 bytes f64, 4 bytes f32); an ALP_RD vector stores its 16-bit left-part exceptions zero-extended
+ * in the same slots.
+ */
+typedef struct alpb200_column {
+	uint64_t          n_vectors;
+	alpb200_vec_meta* meta;            /* [n_vectors] */
+	uint8_t*          packed;          /* 128-byte aligned */
+	uint64_t          packed_capacity; /* bytes */
+	void*             exc_val;         /* [exc_capacity] of the column's value width */
+	uint16_t*         exc_pos;         /* [exc_capacity] */
+	uint64_t          exc_capacity;    /* exception slots */
+	/* [0] packed bytes used, [1] exception slots used, [2] non-zero if a capacity was exceeded (written by
+	 * encode; device memory for the device entry points) */
+	uint64_t*         totals;
+} alpb200_column;
+
+int         alpb200_version(void);
+const char* alpb200_last_error(void);
+/* number of CUDA devices visible to the library; <0 on error.  There is no CPU fallback. */
+int         alpb200_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched device entry points (the hot path).  One warp per 1024-value vector.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Row-group init: first-level sampling + top-k (e,f) search + ALP/ALP_RD decision + RD dictionary.
+ * Replaces alp::encoder<PT>::init (encoder.hpp:420-427), sampler::first_level_sample (sampler.hpp:14-52),
+ * find_top_k_combinations (encoder.hpp:139-235) and alp::rd_encoder<PT>::init / find_best_dictionary
+ * (rd.hpp:89-104,180-185).  n_values must be a multiple of 1024; d_states has ceil(n_vectors/100) entries. */
+int alpb200_rowgroup_init_f64(const double* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* stream);
+int alpb200_rowgroup_init_f32(const float* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* stream);
+
+/* Bytes of scratch alpb200_encode_* needs for n_vectors (decoupled look-back state). */
+size_t alpb200_encode_workspace_bytes(uint64_t n_vectors);
+
+/* Encode n_vectors vectors of d_in into the column (vector i uses d_states[i / 100]).
+ * Replaces, per vector, alp::encoder<PT>::encode (encoder.hpp:402-418) + analyze_ffor (encoder.hpp:109-120)
+ * + ffor::ffor (src/fastlanes_generated_ffor.cpp:29939), or for ALP_RD row-groups
+ * alp::rd_encoder<PT>::encode (rd.hpp:109-147) + 2x ffor::ffor — i.e. test/test_alp_sample.cpp:141-145,164-166. */
+int alpb200_encode_f64(const double* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states,
+                       const alpb200_column* col, void* d_workspace, void* stream);
+int alpb200_encode_f32(const float* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states,
+                       const alpb200_column* col, void* d_workspace, void* stream);
+
+/* Decode vectors [first_vector, first_vector + n_vectors) of the column into d_out (1024 values each).
+ * Replaces generated::falp::fallback::scalar::falp (src/falp.cpp:42440,42644) + alp::decoder<PT>::patch_exceptions
+ * (decoder.hpp:141-149), or for ALP_RD vectors 2x unffor::unffor + alp::rd_encoder<PT>::decode (rd.hpp:152-178)
+ * — i.e. test/test_alp_sample.cpp:148-151,169-170. */
+int alpb200_decode_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_out,
+                       void* stream);
+int alpb200_decode_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, float* d_out,
+                       void* stream);
+
+/* Fused decode + SUM aggregate (no decoded column is written): d_sum[0] += sum of all decoded values, in
+ * vector order per warp and atomically across warps (floating-point addition order is not fixed).
+ * Mirrors the reference's scan primitive `alp_func` + `aggr_plus`
+ * (publication/source_code/bench_end_to_end/src/benchmarks/alp/queries/q1.cpp:63-102). */
+int alpb200_decode_sum_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a host engine calls; copies are part of the call).
+ * A codec context owns device staging buffers, pinned bounce buffers and streams so that repeated
+ * calls do not allocate.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct alpb200_ctx alpb200_ctx;
+
+/* max_vectors: the largest column (in vectors) a call will pass; value_bytes: 8 or 4. */
+int  alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes);
+void alpb200_ctx_destroy(alpb200_ctx* ctx);
+
+/* Compress a host column of n_values (multiple of 1024) values into a host column container whose arrays the
+ * caller allocated (capacities in h_col).  H2D of the values, init, encode, D2H of the compressed arrays.
+ * h_totals[0..1] receive packed bytes / exception slots used. */
+int alpb200_compress_host_f64(alpb200_ctx* ctx, const double* h_in, uint64_t n_values, alpb200_column* h_col);
+int alpb200_compress_host_f32(alpb200_ctx* ctx, const float* h_in, uint64_t n_values, alpb200_column* h_col);
+/* Decompress a host column container into h_out: H2D of the compressed arrays, decode, D2H of the values,
+ * pipelined in chunks of vectors over two streams. */
+int alpb200_decompress_host_f64(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_out);
+int alpb200_decompress_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, float* h_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Single-vector primitives with HOST pointers: the reference's primitive API (PRIMITIVES.md) one call at a
+ * time.  Each call is a 1-vector batch (H2D, one kernel, D2H) and exists for drop-in / parity use, not speed.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* alp::encoder<PT>::encode (encoder.hpp:402-418).  e/f receive stt.exp / stt.fac. */
+int alpb200_prim_encode_f64(const double* h_in, const alpb200_rg_state* h_state, double* h_exc, uint16_t* h_pos,
+                            uint16_t* h_cnt, int64_t* h_enc, uint8_t* e, uint8_t* f);
+int alpb200_prim_encode_f32(const float* h_in, const alpb200_rg_state* h_state, float* h_exc, uint16_t* h_pos,
+                            uint16_t* h_cnt, int32_t* h_enc, uint8_t* e, uint8_t* f);
+/* alp::encoder<PT>::analyze_ffor (encoder.hpp:109-120) */
+int alpb200_prim_analyze_ffor_i64(const int64_t* h_enc, uint8_t* bw, int64_t* base);
+int alpb200_prim_analyze_ffor_i32(const int32_t* h_enc, uint8_t* bw, int32_t* base);
+/* ffor::ffor (include/fastlanes/ffor.hpp:7-15) / unffor::unffor (include/fastlanes/unffor.hpp:7-15).
+ * h_out of ffor receives 128*bw bytes; bw > lane width returns ALPB200_EINVAL (the reference silently no-ops). */
+int alpb200_prim_ffor_u64(const uint64_t* h_in, uint64_t* h_out, uint8_t bw, uint64_t base);
+int alpb200_prim_ffor_u32(const uint32_t* h_in, uint32_t* h_out, uint8_t bw, uint32_t base);
+int alpb200_prim_ffor_u16(const uint16_t* h_in, uint16_t* h_out, uint8_t bw, uint16_t base);
+int alpb200_prim_unffor_u64(const uint64_t* h_in, uint64_t* h_out, uint8_t bw, uint64_t base);
+int alpb200_prim_unffor_u32(const uint32_t* h_in, uint32_t* h_out, uint8_t bw, uint32_t base);
+int alpb200_prim_unffor_u16(const uint16_t* h_in, uint16_t* h_out, uint8_t bw, uint16_t base);
+/* generated::falp::fallback::scalar::falp (include/alp/falp.hpp:10-44): fused unffor + decode.
+ * At bw == lane width the reference's fused kernel is wrong (src/falp.cpp:33311-33319); this entry point has the
+ * unfused semantics unffor + decoder::decode for every width. */
+int alpb200_prim_falp_f64(const uint64_t* h_packed, double* h_out, uint8_t bw, uint64_t base, uint8_t f, uint8_t e);
+int alpb200_prim_falp_f32(const uint32_t* h_packed, float* h_out, uint8_t bw, uint32_t base, uint8_t f, uint8_t e);
+/* alp::decoder<PT>::decode (decoder.hpp:134-138) */
+int alpb200_prim_decode_f64(const int64_t* h_enc, uint8_t f, uint8_t e, double* h_out);
+int alpb200_prim_decode_f32(const int32_t* h_enc, uint8_t f, uint8_t e, float* h_out);
+/* alp::decoder<PT>::patch_exceptions (decoder.hpp:141-149): h_out is read, patched on the device, written back */
+int alpb200_prim_patch_f64(double* h_out, const double* h_exc, const uint16_t* h_pos, uint16_t cnt);
+int alpb200_prim_patch_f32(float* h_out, const float* h_exc, const uint16_t* h_pos, uint16_t cnt);
+/* alp::rd_encoder<PT>::encode (rd.hpp:109-147) / decode (rd.hpp:152-178) */
+int alpb200_prim_rd_encode_f64(const double* h_in, const alpb200_rg_state* h_state, uint16_t* h_exc, uint16_t* h_pos,
+                               uint16_t* h_cnt, uint64_t* h_right, uint16_t* h_left);
+int alpb200_prim_rd_encode_f32(const float* h_in, const alpb200_rg_state* h_state, uint16_t* h_exc, uint16_t* h_pos,
+                               uint16_t* h_cnt, uint32_t* h_right, uint16_t* h_left);
+int alpb200_prim_rd_decode_f64(double* h_out, const uint64_t* h_right, const uint16_t* h_left, const uint16_t* h_exc,
+                               const uint16_t* h_pos, uint16_t cnt, const alpb200_rg_state* h_state);
+int alpb200_prim_rd_decode_f32(float* h_out, const uint32_t* h_right, const uint16_t* h_left, const uint16_t* h_exc,
+                               const uint16_t* h_pos, uint16_t cnt, const alpb200_rg_state* h_state);
+/* alp::encoder<PT>::init (+ rd_encoder<PT>::init when the row-group falls to ALP_RD) on a host column:
+ * the values [offset, min(offset+102400, n_values)) form the row-group. */
+int alpb200_prim_init_f64(const double* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
+int alpb200_prim_init_f32(const float* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic column generators on the device (stateless splitmix64 per index so that
+ * host and device produce identical columns).  kind: 2 = decimal-heavy f64, 3 = high-precision f64 (ALP_RD),
+ * 4 = mixed f32 (f32 entry point only).  first_index lets a shard generate its slice of a global column.
+ * ---------------------------------------------------------------------------------------------- */
+int alpb200_generate_f64(double* d_out, uint64_t n_values, uint64_t first_index, uint64_t seed, int kind, void* stream);
+int alpb200_generate_f32(float* d_out, uint64_t n_values, uint64_t first_index, uint64_t seed, int kind, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALP_B200_H */
