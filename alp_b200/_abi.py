@@ -81,10 +81,11 @@ class Column(ctypes.Structure):
         ("exc_pos", ctypes.c_void_p),
         ("exc_capacity", ctypes.c_uint64),
         ("totals", ctypes.c_void_p),
+        ("max_block_bytes", ctypes.c_uint64),
     ]
 
 
-assert ctypes.sizeof(Column) == 64
+assert ctypes.sizeof(Column) == 72
 
 
 def value_types(value_bytes):
@@ -128,6 +129,7 @@ class HostColumn:
             self.exc_pos.ctypes.data,
             self.exc_val.shape[0],
             self.totals.ctypes.data,
+            int(self.totals[3]),
         )
 
     @property

@@ -1,0 +1,223 @@
+// alp_prims.cuh — single-vector kernels behind the alpb200_prim_* entry points: the reference's primitive API
+// (PRIMITIVES.md) one vector at a time, built from the same device functions as the batched kernels.
+// One warp per launch; these exist for drop-in use and parity tests, not for speed.
+#pragma once
+
+#include "alp_decode.cuh"
+#include "alp_encode.cuh"
+
+namespace alpb200 {
+
+// alp::encoder<PT>::encode (encoder.hpp:402-418): encoded integers + exceptions + positions + count + chosen (e,f)
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_encode_kernel(const PT* __restrict__ in, const alpb200_rg_state* __restrict__ state,
+                                                         typename Traits<PT>::UT* __restrict__ exc, uint16_t* __restrict__ pos,
+                                                         uint16_t* __restrict__ cnt, typename Traits<PT>::UT* __restrict__ enc,
+                                                         uint8_t* __restrict__ ef) {
+	using UT    = typename Traits<PT>::UT;
+	const int t = threadIdx.x;
+	StateRegs st = load_state(state);
+	Analysis<PT> a;
+	analyze_alp<PT>(in, st, t, a);
+#pragma unroll
+	for (int r = 0; r < 32; r++) {
+		enc[Map<PT>::index(t, r)] = a.payload[r];
+	}
+	emit_exceptions<PT>(
+	    a.rowmask, t, [&](uint32_t p) -> UT { return Traits<PT>::bits(in[p]); },
+	    [&](uint32_t rank, uint32_t p, UT val) {
+		    exc[rank] = val;
+		    pos[rank] = (uint16_t)p;
+	    });
+	if (t == 0) {
+		cnt[0] = (uint16_t)a.cnt;
+		ef[0]  = (uint8_t)a.e;
+		ef[1]  = (uint8_t)a.f;
+	}
+}
+
+// alp::encoder<PT>::analyze_ffor (encoder.hpp:109-120)
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_analyze_ffor_kernel(const typename Traits<PT>::ST* __restrict__ enc, uint8_t* __restrict__ bw,
+                                                               typename Traits<PT>::ST* __restrict__ base) {
+	using ST    = typename Traits<PT>::ST;
+	const int t = threadIdx.x;
+	ST        mn = Traits<PT>::ST_MAX, mx = Traits<PT>::ST_MIN;
+	for (int i = t; i < VEC; i += 32) {
+		const ST v = enc[i];
+		mn         = v < mn ? v : mn;
+		mx         = v > mx ? v : mx;
+	}
+	mn = warp_min<ST>(mn);
+	mx = warp_max<ST>(mx);
+	if (t == 0) {
+		bw[0]   = (uint8_t)bits_of_range<PT>(mx, mn);
+		base[0] = mn;
+	}
+}
+
+// ffor::ffor on 64- and 32-bit lanes (include/fastlanes/ffor.hpp:7-8)
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_ffor_kernel(const typename Traits<PT>::UT* __restrict__ in, uint8_t* __restrict__ out,
+                                                       uint32_t bw, typename Traits<PT>::UT base) {
+	using UT = typename Traits<PT>::UT;
+	__shared__ __align__(128) uint8_t blk[64 * 128 + STAGE_PAD];
+	const int t = threadIdx.x;
+	UT        payload[32];
+#pragma unroll
+	for (int r = 0; r < 32; r++) {
+		payload[r] = in[Map<PT>::index(t, r)];
+	}
+	pack_rows(payload, base, bw, t, blk);
+	__syncwarp();
+	const uint4* src = reinterpret_cast<const uint4*>(blk);
+	uint4*       dst = reinterpret_cast<uint4*>(out);
+	for (uint32_t i = t; i < bw * 8u; i += 32) {
+		dst[i] = src[i];
+	}
+}
+
+// ffor / unffor on 16-bit lanes (ffor.hpp:9): 64 lanes x 16 rows, value v = 64*row + lane.  Plain loops.
+__global__ void __launch_bounds__(32) prim_ffor16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t bw,
+                                                         uint16_t base) {
+	const int t = threadIdx.x;
+	if (bw == 0) { return; }
+	const uint32_t mask = bw >= 16 ? 0xFFFFu : ((1u << bw) - 1);
+	for (int lane = t; lane < 64; lane += 32) {
+		uint64_t acc = 0;
+		uint32_t nb = 0, w = 0;
+		for (int row = 0; row < 16; row++) {
+			const uint32_t d = ((uint32_t)(uint16_t)(in[64 * row + lane] - base)) & mask;
+			acc |= (uint64_t)d << nb;
+			nb += bw;
+			while (nb >= 16) {
+				out[64 * w + lane] = (uint16_t)acc;
+				acc >>= 16;
+				nb -= 16;
+				w++;
+			}
+		}
+	}
+}
+__global__ void __launch_bounds__(32) prim_unffor16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t bw,
+                                                           uint16_t base) {
+	__shared__ __align__(128) uint16_t blk[17 * 64];
+	const int t = threadIdx.x;
+	for (uint32_t i = t; i < 17 * 64; i += 32) {
+		blk[i] = i < bw * 64u ? in[i] : (uint16_t)0;
+	}
+	__syncwarp();
+	const uint32_t mask = bw >= 16 ? 0xFFFFu : ((1u << bw) - 1);
+	for (int v = t; v < VEC; v += 32) {
+		const uint32_t d = bw == 0 ? 0u : extract16(blk, v & 63, (v >> 6) * bw, mask);
+		out[v]           = (uint16_t)(d + base);
+	}
+}
+
+// unffor::unffor on 64- and 32-bit lanes (include/fastlanes/unffor.hpp:7-8)
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_unffor_kernel(const uint8_t* __restrict__ in, typename Traits<PT>::UT* __restrict__ out,
+                                                         uint32_t bw, typename Traits<PT>::UT base) {
+	using UT = typename Traits<PT>::UT;
+	__shared__ __align__(128) uint8_t blk[64 * 128 + STAGE_PAD];
+	const int t = threadIdx.x;
+	for (uint32_t i = t; i < bw * 8u; i += 32) {
+		reinterpret_cast<uint4*>(blk)[i] = reinterpret_cast<const uint4*>(in)[i];
+	}
+	__syncwarp();
+	const UT mask = low_mask<UT>(bw);
+	for (int r = 0; r < 32; r++) {
+		UT d = 0;
+		if (bw != 0) {
+			if (sizeof(PT) == 8) {
+				d = (UT)extract64(reinterpret_cast<const uint64_t*>(blk), t & 15, (32u * (t >> 4) + r) * bw, (uint64_t)mask);
+			} else {
+				d = (UT)extract32(reinterpret_cast<const uint32_t*>(blk), t, r * bw, (uint32_t)mask);
+			}
+		}
+		out[Map<PT>::index(t, r)] = d + base;
+	}
+}
+
+// generated::falp::...::falp (include/alp/falp.hpp:10-44) with unfused semantics at every width
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_falp_kernel(const uint8_t* __restrict__ in, PT* __restrict__ out, uint32_t bw,
+                                                       typename Traits<PT>::UT base, uint32_t f, uint32_t e) {
+	__shared__ __align__(128) uint8_t blk[64 * 128 + STAGE_PAD];
+	const int t = threadIdx.x;
+	for (uint32_t i = t; i < bw * 8u; i += 32) {
+		reinterpret_cast<uint4*>(blk)[i] = reinterpret_cast<const uint4*>(in)[i];
+	}
+	__syncwarp();
+	MetaRegs m;
+	const uint64_t b64 = (uint64_t)base;
+	m.a                = make_uint4((uint32_t)b64, (uint32_t)(b64 >> 32), 0, 0);
+	m.b                = make_uint4(0, 0, ((uint32_t)ALPB200_SCHEME_ALP << 16) | (bw << 24), e | (f << 8));
+	decode_alp_vector(blk, m, out, t);
+}
+
+// alp::decoder<PT>::decode (decoder.hpp:134-138)
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_decode_kernel(const typename Traits<PT>::ST* __restrict__ enc, uint32_t f, uint32_t e,
+                                                         PT* __restrict__ out) {
+	using T = Traits<PT>;
+	for (int i = threadIdx.x; i < VEC; i += 32) {
+		out[i] = decode_value<PT>(enc[i], T::fact10(f), T::frac10(e));
+	}
+}
+
+// alp::decoder<PT>::patch_exceptions (decoder.hpp:141-149)
+template <typename UT>
+__global__ void __launch_bounds__(32) prim_patch_kernel(UT* __restrict__ out, const UT* __restrict__ exc, const uint16_t* __restrict__ pos,
+                                                        uint32_t cnt) {
+	for (uint32_t i = threadIdx.x; i < cnt; i += 32) {
+		out[pos[i]] = exc[i];
+	}
+}
+
+// alp::rd_encoder<PT>::encode (rd.hpp:109-147): right parts, dictionary indices (unmasked), left-part exceptions
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_rd_encode_kernel(const PT* __restrict__ in, const alpb200_rg_state* __restrict__ state,
+                                                            uint16_t* __restrict__ exc, uint16_t* __restrict__ pos,
+                                                            uint16_t* __restrict__ cnt, typename Traits<PT>::UT* __restrict__ right,
+                                                            uint16_t* __restrict__ left) {
+	using UT    = typename Traits<PT>::UT;
+	const int t = threadIdx.x;
+	StateRegs st = load_state(state);
+	Analysis<PT> a;
+	analyze_rd<PT>(in, state, st, t, a, [&](int r, uint32_t idx) { left[Map<PT>::index(t, r)] = (uint16_t)idx; });
+#pragma unroll
+	for (int r = 0; r < 32; r++) {
+		right[Map<PT>::index(t, r)] = a.payload[r];
+	}
+	const uint32_t rbw = a.bw;
+	emit_exceptions<PT>(
+	    a.rowmask, t, [&](uint32_t p) -> UT { return (UT)(Traits<PT>::bits(in[p]) >> rbw); },
+	    [&](uint32_t rank, uint32_t p, UT val) {
+		    exc[rank] = (uint16_t)val;
+		    pos[rank] = (uint16_t)p;
+	    });
+	if (t == 0) { cnt[0] = (uint16_t)a.cnt; }
+}
+
+// alp::rd_encoder<PT>::decode (rd.hpp:152-178) on unpacked right parts / dictionary indices
+template <typename PT>
+__global__ void __launch_bounds__(32) prim_rd_decode_kernel(typename Traits<PT>::UT* __restrict__ out,
+                                                            const typename Traits<PT>::UT* __restrict__ right,
+                                                            const uint16_t* __restrict__ left, const uint16_t* __restrict__ exc,
+                                                            const uint16_t* __restrict__ pos, uint32_t cnt,
+                                                            const alpb200_rg_state* __restrict__ state) {
+	using UT    = typename Traits<PT>::UT;
+	const int t = threadIdx.x;
+	StateRegs st = load_state(state);
+	const uint32_t rbw = st.right_bw();
+	for (int i = t; i < VEC; i += 32) {
+		out[i] = ((UT)dict_lookup(st.dict, left[i] & 7u) << rbw) | right[i];
+	}
+	__syncwarp();
+	for (uint32_t i = t; i < cnt; i += 32) {
+		out[pos[i]] = ((UT)exc[i] << rbw) | right[pos[i]];
+	}
+}
+
+}  // namespace alpb200

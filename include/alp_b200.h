@@ -106,12 +106,17 @@ typedef struct alpb200_column {
 	void*             exc_val;         /* [exc_capacity] of the column's value width */
 	uint16_t*         exc_pos;         /* [exc_capacity] */
 	uint64_t          exc_capacity;    /* exception slots */
-	/* [0] packed bytes used, [1] exception slots used, [2] non-zero if a capacity was exceeded (written by
-	 * encode; device memory for the device entry points) */
+	/* [0] packed bytes used, [1] exception slots used, [2] non-zero if a capacity was exceeded, [3] largest packed
+	 * block of any vector in bytes (written by encode; device memory for the device entry points) */
 	uint64_t*         totals;
+	/* decode hint: the largest packed block of any vector in bytes (totals[3] after encode), or 0 when unknown —
+	 * the decoder then sizes its shared-memory stages for the widest possible block */
+	uint64_t          max_block_bytes;
 } alpb200_column;
 
 int         alpb200_version(void);
+/* sizeof(alpb200_rg_state), sizeof(alpb200_vec_meta), sizeof(alpb200_column) as compiled into the library */
+void        alpb200_abi_sizes(uint32_t out[3]);
 const char* alpb200_last_error(void);
 /* number of CUDA devices visible to the library; <0 on error.  There is no CPU fallback. */
 int         alpb200_device_count(void);
@@ -124,8 +129,12 @@ int         alpb200_device_count(void);
  * Replaces alp::encoder<PT>::init (encoder.hpp:420-427), sampler::first_level_sample (sampler.hpp:14-52),
  * find_top_k_combinations (encoder.hpp:139-235) and alp::rd_encoder<PT>::init / find_best_dictionary
  * (rd.hpp:89-104,180-185).  n_values must be a multiple of 1024; d_states has ceil(n_vectors/100) entries. */
-int alpb200_rowgroup_init_f64(const double* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* stream);
-int alpb200_rowgroup_init_f32(const float* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* stream);
+int alpb200_rowgroup_init_f64(const double* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* d_workspace,
+                              void* stream);
+int alpb200_rowgroup_init_f32(const float* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* d_workspace,
+                              void* stream);
+/* Bytes of scratch alpb200_rowgroup_init_* needs for n_values (per-sampled-vector search results). */
+size_t alpb200_init_workspace_bytes(uint64_t n_values);
 
 /* Bytes of scratch alpb200_encode_* needs for n_vectors (decoupled look-back state). */
 size_t alpb200_encode_workspace_bytes(uint64_t n_vectors);
@@ -148,13 +157,6 @@ int alpb200_decode_f64(const alpb200_column* col, uint64_t first_vector, uint64_
 int alpb200_decode_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, float* d_out,
                        void* stream);
 
-/* Fused decode + SUM aggregate (no decoded column is written): d_sum[0] += sum of all decoded values, in
- * vector order per warp and atomically across warps (floating-point addition order is not fixed).
- * Mirrors the reference's scan primitive `alp_func` + `aggr_plus`
- * (publication/source_code/bench_end_to_end/src/benchmarks/alp/queries/q1.cpp:63-102). */
-int alpb200_decode_sum_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum,
-                           void* stream);
-
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host engine calls; copies are part of the call).
  * A codec context owns device staging buffers, pinned bounce buffers and streams so that repeated
@@ -175,6 +177,9 @@ int alpb200_compress_host_f32(alpb200_ctx* ctx, const float* h_in, uint64_t n_va
  * pipelined in chunks of vectors over two streams. */
 int alpb200_decompress_host_f64(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_out);
 int alpb200_decompress_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, float* h_out);
+/* Page-locked host memory for the buffers handed to the *_host entry points (pageable buffers also work, slower). */
+void* alpb200_host_alloc(size_t bytes);
+void  alpb200_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------------
  * Single-vector primitives with HOST pointers: the reference's primitive API (PRIMITIVES.md) one call at a

@@ -1,0 +1,252 @@
+"""GPU parity of the batched hot path (alpb200_rowgroup_init / encode / decode) on whole columns.
+
+Ground truth is (a) the committed golden fixtures produced by the unmodified reference (tests/golden/) and (b) the CPU
+checker that travels with the repository (oracle/_ref when built, else the C restatement).  Integer / byte work must
+be bit exact: metadata records, packed blocks, exception values and positions, and the decoded values.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import host_column_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    import torch
+
+    return torch.device("cuda:0")
+
+
+def _bits(t):
+    import torch
+
+    return t.view(torch.int64 if t.element_size() == 8 else torch.int32)
+
+
+def _meta_fields_equal(a, b, name):
+    for key in ("packed_off", "exc_off", "exc_cnt", "scheme", "bw", "e", "f"):
+        assert np.array_equal(a[key], b[key]), (name, key)
+    alp = a["scheme"] == 2
+    assert np.array_equal(a["base"][alp], b["base"][alp]), (name, "base")
+    assert a[~alp].tobytes() == b[~alp].tobytes() or np.array_equal(
+        a[~alp].view(np.uint8).reshape(-1, 32)[:, :16], b[~alp].view(np.uint8).reshape(-1, 32)[:, :16]
+    ), (name, "rd_dict")
+
+
+def _assert_columns_equal(got, want, name):
+    """got, want: HostColumn.  Everything the decoder reads must be byte-identical."""
+    assert got.n_vectors == want.n_vectors
+    assert got.packed_bytes == want.packed_bytes and got.n_exceptions == want.n_exceptions, name
+    _meta_fields_equal(got.meta, want.meta, name)
+    assert got.packed[: got.packed_bytes].tobytes() == want.packed[: want.packed_bytes].tobytes(), (name, "packed")
+    n = got.n_exceptions
+    assert got.exc_pos[:n].tobytes() == want.exc_pos[:n].tobytes(), (name, "exc_pos")
+    assert got.exc_val[:n].tobytes() == want.exc_val[:n].tobytes(), (name, "exc_val")
+
+
+@pytest.mark.parametrize("name", ["city_temperature_f_tw", "food_prices_tw", "gov26_tw"])
+def test_real_columns_against_golden(name, golden_columns):
+    """128 vectors = 2 row-groups of real data with many distinct (bw, e, f) per column."""
+    import torch
+
+    import alp_b200
+
+    gc = golden_columns
+    x = gc[name + "_input"]
+    ref_col = host_column_from_golden(gc, name)
+    xd = torch.from_numpy(x).to(_dev())
+
+    # decode of the reference-encoded column
+    y = alp_b200.decode(alp_b200.DeviceColumn.from_host(ref_col, _dev()))
+    assert y.cpu().numpy().tobytes() == x.tobytes()
+
+    # device init == reference init (ALP columns: no STL-dependent ties)
+    states = alp_b200.rowgroup_init(xd).cpu().numpy().view(alp_b200._abi.RG_STATE_DTYPE).reshape(-1)
+    assert states.tobytes() == gc[name + "_states"].tobytes()
+
+    # device encode == reference encode, byte for byte
+    col = alp_b200.encode(xd)
+    _assert_columns_equal(col.to_host(), ref_col, name)
+    assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd))
+
+    # partial decode of a vector range
+    part = alp_b200.decode(col, first=37, n=50)
+    assert torch.equal(_bits(part), _bits(xd[37 * 1024 : 87 * 1024]))
+
+
+@pytest.mark.parametrize("kind,name", [(2, "synthetic_decimal_f64"), (3, "synthetic_highprec_f64"), (4, "synthetic_mixed_f32")])
+def test_synthetic_columns_against_golden(kind, name, golden_columns, port):
+    """The three synthetic generators of SURVEY.md §8d, 4 row-groups each: generator, init, metadata and payload
+    digests against what the reference produced."""
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    gc = golden_columns
+    entry = [e for e in gc.index if e["name"] == name][0]
+    n = entry["n_values"]
+    xd = alp_b200.generate(n, kind, _dev())
+    x = xd.cpu().numpy()
+    assert x.tobytes() == pyoracle.generate(n, kind).tobytes()
+    assert [float(v) for v in x[:4]] == entry["first_values"]
+    assert int(np.bitwise_xor.reduce(x.view(np.uint64 if kind != 4 else np.uint32))) == entry["xor_checksum"]
+
+    states = alp_b200.rowgroup_init(xd)
+    col = alp_b200.encode(xd, states)
+    h = col.to_host()
+    want_meta = gc[name + "_meta"]
+    assert h.packed_bytes == int(gc[name + "_totals"][0])
+    # (for ALP_RD the number of exceptions depends on which of several equally frequent left parts made it into the
+    # dictionary — STL-defined in the reference, rd.hpp:35-54 — so it is only compared for ALP columns)
+    assert kind == 3 or h.n_exceptions == int(gc[name + "_totals"][1])
+    if kind != 3:
+        # ALP: everything is determined — metadata and payload digests equal the reference's
+        _meta_fields_equal(h.meta, want_meta, name)
+        sha = entry["sha256"]
+        assert hashlib.sha256(h.packed[: h.packed_bytes].tobytes()).hexdigest() == sha["packed"]
+        assert hashlib.sha256(h.exc_val[: h.n_exceptions].tobytes()).hexdigest() == sha["exc_val"]
+        assert hashlib.sha256(h.exc_pos[: h.n_exceptions].tobytes()).hexdigest() == sha["exc_pos"]
+        st = states.cpu().numpy().view(alp_b200._abi.RG_STATE_DTYPE).reshape(-1)
+        assert st.tobytes() == gc[name + "_states"].tobytes()
+    else:
+        # ALP_RD: cut, widths, dictionary size and sizes equal the reference's; dictionary order on ties is this
+        # library's rule (shared with the restatement), so compare the full stream with the restatement
+        for key in ("scheme", "bw", "e", "f", "packed_off"):
+            assert np.array_equal(h.meta[key], want_meta[key]), key
+        _assert_columns_equal(h, port.encode_column(x), name)
+    assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd))
+
+
+def test_cross_decode_with_checker(checker):
+    """GPU-encoded columns decode on the CPU checker and vice versa (mixed ALP / ALP_RD row-groups in one column)."""
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    x = np.concatenate([pyoracle.generate(102400, 2), pyoracle.generate(102400, 3), pyoracle.generate(51200, 2, first_index=7)])
+    xd = torch.from_numpy(x).to(_dev())
+    col = alp_b200.encode(xd)
+    h = col.to_host()
+    assert set(h.meta["scheme"].tolist()) == {1, 2}
+    assert checker.decode_column(h).tobytes() == x.tobytes()
+    ref_col = checker.encode_column(x)
+    y = alp_b200.decode(alp_b200.DeviceColumn.from_host(ref_col, _dev()))
+    assert y.cpu().numpy().tobytes() == x.tobytes()
+    assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd))
+
+
+def test_reference_state_gives_reference_stream_for_rd(reference):
+    """Fed the reference's own row-group states (dictionary order and exception indices included), the device encoder
+    reproduces the reference's ALP_RD stream byte for byte."""
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    x = pyoracle.generate(3 * 102400, 3)
+    states = np.concatenate([reference.init(x, off) for off in range(0, x.shape[0], 102400)])
+    sd = torch.from_numpy(states.view(np.uint8).reshape(len(states), -1)).to(_dev())
+    col = alp_b200.encode(torch.from_numpy(x).to(_dev()), sd)
+    _assert_columns_equal(col.to_host(), reference.encode_column(x), "rd-with-reference-state")
+
+
+def test_edge_shapes(checker):
+    """One vector, a ragged last row-group, all-equal values, all exceptions, every special value."""
+    import torch
+
+    import alp_b200
+
+    rng = np.random.default_rng(3)
+    cols = {
+        "one_vector": np.round(rng.normal(20, 5, 1024), 2),
+        "ragged_rowgroup": np.round(rng.normal(20, 5, 1024 * 137), 1),
+        "constant": np.full(1024 * 3, 10.23),
+        "all_nan": np.full(1024 * 2, np.nan),
+        "zeros_f32": np.zeros(1024 * 2, dtype=np.float32),
+        "specials_f32": np.tile(np.array([np.nan, np.inf, -np.inf, -0.0, 0.0, 1.5, 3e38, 2147483648.0], dtype=np.float32), 128 * 3),
+        "random_bits_f64": rng.integers(0, 1 << 63, size=1024 * 101, dtype=np.uint64).view(np.float64),
+        "random_bits_f32": rng.integers(0, 1 << 32, size=1024 * 101, dtype=np.uint64).astype(np.uint32).view(np.float32),
+    }
+    for name, x in cols.items():
+        xd = torch.from_numpy(x).to(_dev())
+        col = alp_b200.encode(xd)
+        assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd)), name
+        h = col.to_host()
+        assert checker.decode_column(h).tobytes() == x.tobytes(), name
+        want = checker.encode_column(x)
+        if set(want.meta["scheme"].tolist()) == {2}:
+            _assert_columns_equal(h, want, name)
+
+
+def test_capacity_overflow_is_reported():
+    import torch
+
+    import alp_b200
+
+    x = alp_b200.generate(1024 * 64, 2, _dev())
+    col = alp_b200.DeviceColumn(64, 8, _dev(), packed_capacity=1024, exc_capacity=4)
+    alp_b200.encode(x, col=col)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        col.read_totals()
+
+
+def test_empty_and_bad_arguments():
+    import torch
+
+    import alp_b200
+
+    with pytest.raises(ValueError):
+        alp_b200.encode(torch.zeros(1000, dtype=torch.float64, device=_dev()))
+    col = alp_b200.encode(alp_b200.generate(2048, 2, _dev()))
+    with pytest.raises(alp_b200.AlpError):
+        alp_b200.decode(col, first=1, n=5)
+    assert alp_b200.decode(col, first=2, n=0).numel() == 0
+
+
+@pytest.mark.parametrize("kind", [2, 3, 4])
+def test_host_codec_round_trip(kind, checker):
+    """alpb200_compress_host / decompress_host: host buffers in, host buffers out (copies inside the call)."""
+    import alp_b200
+    from oracle import pyoracle
+
+    n = 3 * 102400 + 17 * 1024
+    x = pyoracle.generate(n, kind)
+    codec = alp_b200.HostCodec(n // 1024, x.dtype.itemsize)
+    col = codec.compress(x)
+    assert checker.decode_column(col).tobytes() == x.tobytes()
+    assert codec.decompress(col).tobytes() == x.tobytes()
+    assert codec.decompress(checker.encode_column(x)).tobytes() == x.tobytes()
+    codec.close()
+
+
+def test_large_column_properties():
+    """2^26 values (BASELINE config 2 at 1/16 scale; the full size runs in bench.py, which verifies its round trip
+    too): encode→decode is the identity, sizes match the per-vector metadata, positions are sorted, blocks are dense."""
+    import torch
+
+    import alp_b200
+
+    n = 1 << 26
+    xd = alp_b200.generate(n, 2, _dev())
+    col = alp_b200.encode(xd)
+    packed_bytes, n_exc = col.read_totals()
+    y = alp_b200.decode(col)
+    assert torch.equal(_bits(y), _bits(xd))
+    meta = col.meta.cpu().numpy().view(alp_b200._abi.VEC_META_DTYPE).reshape(-1)
+    units = meta["bw"].astype(np.int64)
+    assert np.array_equal(meta["packed_off"].astype(np.int64), np.concatenate([[0], np.cumsum(units)[:-1]]))
+    assert packed_bytes == int(units.sum()) * 128
+    cnt = meta["exc_cnt"].astype(np.int64)
+    assert np.array_equal(meta["exc_off"].astype(np.int64), np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+    assert n_exc == int(cnt.sum())
+    assert set(meta["bw"].tolist()) == {20}  # every vector of the decimal column packs to 20 bits
+    pos = col.exc_pos[:n_exc].cpu().numpy().view(np.uint16).astype(np.int64)
+    owner = np.repeat(np.arange(meta.shape[0]), cnt)
+    key = owner * 1024 + pos
+    assert np.all(np.diff(key) > 0)  # ascending positions inside every vector, vectors in order
