@@ -64,9 +64,10 @@ int device_info(DeviceInfo& out) {
 
 template <typename PT>
 int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_out, void* stream) {
-	if (!col || !d_out) { return fail(ALPB200_EINVAL, "decode: null argument"); }
+	if (!col) { return fail(ALPB200_EINVAL, "decode: null argument"); }
 	if (first + n > col->n_vectors) { return fail(ALPB200_EINVAL, "decode: vector range outside the column"); }
 	if (n == 0) { return ALPB200_OK; }
+	if (!d_out || !col->meta || !col->packed) { return fail(ALPB200_EINVAL, "decode: null argument"); }
 	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0) { return fail(ALPB200_EINVAL, "decode: column.packed must be 128-byte aligned"); }
 	DeviceInfo di;
 	if (int rc = device_info(di)) { return rc; }
