@@ -90,7 +90,7 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 
 size_t encode_workspace_bytes(uint64_t n_vectors) {
 	const uint64_t blocks = (n_vectors + ENC_WARPS - 1) / ENC_WARPS;
-	return (size_t)((2 + blocks) * sizeof(uint64_t) + 255) & ~(size_t)255;
+	return (size_t)((2 + 2 * blocks) * sizeof(uint64_t) + 255) & ~(size_t)255;
 }
 
 template <typename PT>
@@ -105,7 +105,7 @@ int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, 
 	CUDA_TRY(cudaMemsetAsync(ws, 0, encode_workspace_bytes(n), s));
 	CUDA_TRY(cudaMemsetAsync(col->totals, 0, 4 * sizeof(uint64_t), s));
 	if (n == 0) { return ALPB200_OK; }
-	constexpr size_t smem = (size_t)ENC_WARPS * (sizeof(PT) == 8 ? 66u : 35u) * 128u;
+	constexpr size_t smem = (size_t)ENC_WARPS * VEC * sizeof(PT);  // one [32][32] tile per warp
 	auto             kern = encode_kernel<PT, ENC_WARPS>;
 	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	ColOut         out {col->meta, col->packed, col->packed_capacity, col->exc_val, col->exc_pos, col->exc_capacity, col->totals};

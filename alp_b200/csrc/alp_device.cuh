@@ -82,7 +82,8 @@ struct Traits<double> {
 	}
 	// x86 cvttsd2si: NaN / out-of-range → 0x8000000000000000 (PTX cvt.rzi would saturate and map NaN to 0)
 	__device__ static __forceinline__ int64_t cast_x86(double t) {
-		return (t >= -9223372036854775808.0 && t < 9223372036854775808.0) ? __double2ll_rz(t) : INT64_MIN;
+		// |t| < 2^63 is false for NaN and for t == -2^63, whose conversion is INT64_MIN anyway
+		return fabs(t) < 9223372036854775808.0 ? __double2ll_rz(t) : INT64_MIN;
 	}
 	__device__ static __forceinline__ double to_float(int64_t x) { return __ll2double_rn(x); }
 	__device__ static __forceinline__ uint64_t bits(double v) { return (uint64_t)__double_as_longlong(v); }
@@ -117,7 +118,7 @@ struct Traits<float> {
 	__device__ static __forceinline__ float magic_round(float t) { return __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f); }
 	// x86 cvttss2si (32-bit destination)
 	__device__ static __forceinline__ int32_t cast_x86(float t) {
-		return (t >= -2147483648.0f && t < 2147483648.0f) ? __float2int_rz(t) : INT32_MIN;
+		return fabsf(t) < 2147483648.0f ? __float2int_rz(t) : INT32_MIN;
 	}
 	__device__ static __forceinline__ float to_float(int32_t x) { return __int2float_rn(x); }
 	__device__ static __forceinline__ uint32_t bits(float v) { return __float_as_uint(v); }

@@ -5,13 +5,19 @@
 // ALP_RD row-groups alp::rd_encoder<PT>::encode (include/alp/rd.hpp:109-147) + two ffor::ffor calls
 // (test/test_alp_sample.cpp:141-145,164-166).
 //
-// Register-resident: a thread keeps its 32 encoded integers in registers from the input load to the bit-packer.
-// 64-bit lanes: thread (lane = t&15, half = t>>4) owns rows 32*half .. 32*half+31 of FastLanes lane `lane`, i.e. values
-// 16*(32*half + r) + lane — exactly half of that lane's bit stream, which is bw whole 32-bit words.
-// 32-bit lanes: thread t owns lane t, values 32*r + t.
-// The packed block is assembled in shared memory in its final (verbatim) layout and leaves with one bulk-async
-// store (TMA 1-D).  Output offsets come from a single-pass decoupled look-back over thread blocks, so the column is
-// written contiguously, in vector order, in the same pass that reads the input.
+// Thread -> value mapping.  64-bit lanes: thread (lane = t&15, half = t>>4) owns rows 32*half .. 32*half+31 of FastLanes
+// lane `lane`, i.e. values 16*(32*half + r) + lane — exactly half of that lane's bit stream, which is bw whole 32-bit
+// words.  32-bit lanes: thread t owns lane t, values 32*r + t.  Every warp load instruction reads full 128-byte lines.
+//
+// Phases of a warp:
+//   1 analysis   stream the vector once (double-buffered batches of 8 rows), encode + decode + compare per value,
+//                track min/max of the non-exceptions and a per-thread exception bitmap; the encoded integers are
+//                parked in a per-warp shared-memory tile ([row][thread], conflict-free) instead of 64 registers
+//   2 placement  the block's packed size and exception count join a single-pass decoupled look-back over thread
+//                blocks (tickets are handed out in launch order), so the column comes out contiguous and in vector order
+//   3 packing    FFOR straight from the tile into the final interleaved layout: each thread assembles whole 64-bit
+//                words of its lane's stream and the warp stores full 128-byte lines; then exceptions in position order
+//                and the 32-byte record
 #pragma once
 
 #include "alp_device.cuh"
@@ -24,10 +30,15 @@ struct Map;
 template <>
 struct Map<double> {
 	__device__ static __forceinline__ int index(int t, int r) { return 512 * (t >> 4) + 16 * r + (t & 15); }
+	// thread and row that own value index v
+	__device__ static __forceinline__ int thread_of(int v) { return (v & 15) + 16 * (v >> 9); }
+	__device__ static __forceinline__ int row_of(int v) { return (v >> 4) & 31; }
 };
 template <>
 struct Map<float> {
 	__device__ static __forceinline__ int index(int t, int r) { return 32 * r + t; }
+	__device__ static __forceinline__ int thread_of(int v) { return v & 31; }
+	__device__ static __forceinline__ int row_of(int v) { return v >> 5; }
 };
 
 // the head of alpb200_rg_state (44 bytes), loaded once per warp
@@ -55,32 +66,39 @@ __device__ __forceinline__ StateRegs load_state(const alpb200_rg_state* s) {
 	return r;
 }
 
-// what a warp knows about its vector after the analysis phase
+// What a warp knows about its vector after the analysis phase.  The payload (ALP: encoded integers, ALP_RD: right
+// parts) sits in the warp's shared-memory tile: element [r*32 + t] belongs to thread t, row r.
 template <typename PT>
 struct Analysis {
-	typename Traits<PT>::UT payload[32];  // ALP: encoded integers (exceptions already overwritten by the fill value);
-	                                      // ALP_RD: right parts
-	uint32_t left_nib[4];                 // ALP_RD: dictionary index of row r in nibble r (already masked to left_bw)
-	uint32_t rowmask;                     // lane r: ballot of "is exception" over row r
-	uint32_t cnt;                         // exceptions in the vector
-	uint32_t bw;                          // ALP: FFOR width; ALP_RD: right width
-	uint32_t e, f;                        // ALP: exponent/factor;  ALP_RD: left width / dictionary size
-	typename Traits<PT>::ST base;         // ALP FOR base (0 for ALP_RD)
+	uint32_t left_nib[4];          // ALP_RD: dictionary index of row r in nibble r (already masked to left_bw)
+	uint32_t myexc;                // bit r: this thread's value in row r is an exception
+	uint32_t cnt;                  // exceptions in the vector
+	uint32_t bw;                   // ALP: FFOR width; ALP_RD: right width
+	uint32_t e, f;                 // ALP: exponent/factor;  ALP_RD: left width / dictionary size
+	typename Traits<PT>::ST base;  // ALP FOR base (0 for ALP_RD)
+	typename Traits<PT>::ST fill;  // ALP: value stored at exception positions (encoder.hpp:382-393)
 };
 
+// 32x32 bit-matrix transpose across the warp: in = bit r of lane t, out = bit t of lane r.
+// Turns the per-thread exception bitmaps into per-row ballots (what the position-ordered emission needs).
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int t) {
+	uint32_t m = 0x0000FFFFu;
+#pragma unroll
+	for (int j = 16; j > 0; j >>= 1) {
+		const uint32_t y = __shfl_xor_sync(FULL, x, j);
+		x                = (t & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+		m ^= m << (j >> 1);
+	}
+	return x;
+}
+
 // ---- second-level sampling: encoder.hpp:241-305 --------------------------------------------------------------------
+// xs = this lane's sample, value 32*lane of the vector (samples 0, 32, ..., 992; encoder.hpp:253-254,266)
 template <typename PT>
-__device__ __forceinline__ void choose_exponent_factor(const PT* __restrict__ in_vec, const StateRegs& st, int t, int& e_out,
-                                                       int& f_out) {
+__device__ __forceinline__ void choose_exponent_factor(PT xs, const StateRegs& st, int& e_out, int& f_out) {
 	using T  = Traits<PT>;
 	using ST = typename T::ST;
-	if (st.k <= 1) {  // encoder.hpp:409-412
-		e_out = st.exp_of(0);
-		f_out = st.fac_of(0);
-		return;
-	}
-	const PT xs      = in_vec[32 * t];  // samples 0, 32, ..., 992 (encoder.hpp:253-254,266)
-	int      best_e  = 0, best_f = 0, worse = 0;
+	int      best_e  = st.exp_of(0), best_f = st.fac_of(0), worse = 0;
 	uint32_t best_sz = 0;
 	for (int k = 0; k < (int)st.k; k++) {
 		const int e = st.exp_of(k), f = st.fac_of(k);
@@ -93,8 +111,6 @@ __device__ __forceinline__ void choose_exponent_factor(const PT* __restrict__ in
 		const uint32_t sz    = 32u * bits_of_range<PT>(mx, mn) + n_exc * (T::EXC_BITS + 16);
 		if (k == 0) {
 			best_sz = sz;
-			best_e  = e;
-			best_f  = f;
 			continue;
 		}
 		if (sz >= best_sz) {
@@ -112,80 +128,91 @@ __device__ __forceinline__ void choose_exponent_factor(const PT* __restrict__ in
 
 // ---- ALP analysis: encoder.hpp:307-400 + :109-120 ------------------------------------------------------------------
 template <typename PT>
-__device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const StateRegs& st, int t, Analysis<PT>& a) {
+__device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const StateRegs& st, int t,
+                                            typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a) {
 	using T  = Traits<PT>;
 	using UT = typename T::UT;
 	using ST = typename T::ST;
-	PT x[32];
+	constexpr int B = 8;  // rows per batch
+	PT x[B], nx[B];
 #pragma unroll
-	for (int r = 0; r < 32; r++) {
-		x[r] = in_vec[Map<PT>::index(t, r)];
+	for (int i = 0; i < B; i++) {
+		x[i] = in_vec[Map<PT>::index(t, i)];
 	}
-	int e, f;
-	choose_exponent_factor<PT>(in_vec, st, t, e, f);
+	int e = st.exp_of(0), f = st.fac_of(0);
+	if (st.k > 1) { choose_exponent_factor<PT>(in_vec[32 * t], st, e, f); }  // encoder.hpp:409-412
 	const PT ex = T::exp10(e), frf = T::frac10(f), fre = T::frac10(e);
 	const ST fa = T::fact10(f);
 
-	uint32_t myexc = 0, rowmask = 0;
+	uint32_t myexc = 0;
+	ST       mn = T::ST_MAX, mx = T::ST_MIN;
+#pragma unroll 1
+	for (int r0 = 0; r0 < 32; r0 += B) {
+		if (r0 + B < 32) {
 #pragma unroll
-	for (int r = 0; r < 32; r++) {
-		const PT   v   = T::is_special(T::bits(x[r])) ? T::upper_limit() : x[r];  // encoder.hpp:326-338
-		const ST   enc = encode_value<PT, false>(v, ex, frf);                     // :345
-		const PT   dec = decode_value<PT>(enc, fa, fre);                          // :347
-		const bool exc = dec != v;                                                // :374-379
-		a.payload[r]   = (UT)enc;
-		myexc |= (uint32_t)exc << r;
-		const uint32_t m = __ballot_sync(FULL, exc);
-		if (t == r) { rowmask = m; }
+			for (int i = 0; i < B; i++) {
+				nx[i] = in_vec[Map<PT>::index(t, r0 + B + i)];
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < B; i++) {
+			// encoder.hpp:326-349,374-379.  The reference first replaces special values (double: -0.0; float: NaN, ±Inf,
+			// -0.0) by ENCODING_UPPER_LIMIT, which never round-trips; flagging them directly is the same outcome — an
+			// exception whose slot is later overwritten by the fill value.
+			const ST   enc = encode_value<PT, false>(x[i], ex, frf);
+			const PT   dec = decode_value<PT>(enc, fa, fre);
+			const bool exc = (dec != x[i]) || T::is_special(T::bits(x[i]));
+			tile[(r0 + i) * 32 + t] = (UT)enc;
+			myexc |= (uint32_t)exc << (r0 + i);
+			const ST lo = exc ? T::ST_MAX : enc, hi = exc ? T::ST_MIN : enc;
+			mn          = lo < mn ? lo : mn;
+			mx          = hi > mx ? hi : mx;
+		}
+		if (r0 + B < 32) {
+#pragma unroll
+			for (int i = 0; i < B; i++) {
+				x[i] = nx[i];
+			}
+		}
 	}
+	a.myexc = myexc;
+	a.cnt   = __reduce_add_sync(FULL, (uint32_t)__popc(myexc));
 	// fill value = encoded integer at the first non-exception position, 0 if there is none (encoder.hpp:382-388)
 	uint32_t cand = 0xFFFFu;
-	if (sizeof(PT) == 8) {
-		const uint32_t lo = ~rowmask & 0xFFFFu, hi = (~rowmask) >> 16;
-		if (lo) { cand = 16u * t + (__ffs(lo) - 1); }
-		if (hi) { cand = min(cand, 16u * (32 + t) + (__ffs(hi) - 1)); }
+	if (~myexc) { cand = (uint32_t)Map<PT>::index(t, __ffs((int)~myexc) - 1); }
+	cand   = __reduce_min_sync(FULL, cand);
+	a.fill = 0;
+	__syncwarp();
+	if (cand != 0xFFFFu) {
+		a.fill = (ST)tile[Map<PT>::row_of((int)cand) * 32 + Map<PT>::thread_of((int)cand)];
+		mn     = warp_min<ST>(mn);  // analyze_ffor (encoder.hpp:109-120): exceptions hold `fill`, itself a non-exception
+		mx     = warp_max<ST>(mx);
 	} else {
-		if (~rowmask) { cand = 32u * t + (__ffs(~rowmask) - 1); }
+		mn = mx = 0;
 	}
-	cand    = __reduce_min_sync(FULL, cand);
-	ST fill = 0;
-	if (cand != 0xFFFFu) { fill = encode_value<PT, false>(in_vec[cand], ex, frf); }
-	ST mn = T::ST_MAX, mx = T::ST_MIN;
-#pragma unroll
-	for (int r = 0; r < 32; r++) {
-		ST v = (ST)a.payload[r];
-		if ((myexc >> r) & 1u) { v = fill; }  // encoder.hpp:393
-		a.payload[r] = (UT)v;
-		mn           = v < mn ? v : mn;
-		mx           = v > mx ? v : mx;
-	}
-	mn        = warp_min<ST>(mn);  // analyze_ffor, encoder.hpp:109-120
-	mx        = warp_max<ST>(mx);
-	a.rowmask = rowmask;
-	a.cnt     = __reduce_add_sync(FULL, (uint32_t)__popc(rowmask));
-	a.bw      = (uint32_t)bits_of_range<PT>(mx, mn);
-	a.base    = mn;
-	a.e       = (uint32_t)e;
-	a.f       = (uint32_t)f;
+	a.bw   = (uint32_t)bits_of_range<PT>(mx, mn);
+	a.base = mn;
+	a.e    = (uint32_t)e;
+	a.f    = (uint32_t)f;
 }
 
 // ---- ALP_RD analysis: rd.hpp:109-147 --------------------------------------------------------------------------------
 // on_index(r, idx) reports the unmasked dictionary index of row r (what rd.hpp:136 stores before FFOR masks it).
 template <typename PT, typename OnIndex>
 __device__ __forceinline__ void analyze_rd(const PT* __restrict__ in_vec, const alpb200_rg_state* state, const StateRegs& st,
-                                           int t, Analysis<PT>& a, OnIndex&& on_index) {
+                                           int t, typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a, OnIndex&& on_index) {
 	using T              = Traits<PT>;
 	using UT             = typename T::UT;
 	const uint32_t rbw   = st.right_bw(), lbw = st.left_bw(), ds = st.dict_size();
 	const UT       rmask = low_mask<UT>(rbw);
 	const uint32_t lmask = (1u << lbw) - 1;
-	uint32_t       rowmask = 0;
+	uint32_t       myexc = 0;
 	a.left_nib[0] = a.left_nib[1] = a.left_nib[2] = a.left_nib[3] = 0;
-#pragma unroll
+#pragma unroll 8
 	for (int r = 0; r < 32; r++) {
 		const UT       bits = T::bits(in_vec[Map<PT>::index(t, r)]);
 		const uint32_t left = (uint32_t)(bits >> rbw);
-		a.payload[r]        = bits & rmask;
+		tile[r * 32 + t]    = bits & rmask;
 		uint32_t idx = ds;  // rd.hpp:129-131: a left part nobody has seen gets the smallest non-dictionary index
 		bool     hit = false;
 #pragma unroll
@@ -195,28 +222,25 @@ __device__ __forceinline__ void analyze_rd(const PT* __restrict__ in_vec, const 
 				hit = true;
 			}
 		}
-		if (st.n_extra != 0 && __any_sync(FULL, !hit)) {  // rd.hpp:73-77,133: sampled left parts outside the dictionary
-			if (!hit) {
-				for (uint32_t x = 0; x < st.n_extra; x++) {
-					if (state->extra_key[x] == left) {
-						idx = state->extra_idx[x];
-						break;
-					}
+		if (st.n_extra != 0 && !hit) {  // rd.hpp:73-77,133: sampled left parts outside the dictionary
+			for (uint32_t x = 0; x < st.n_extra; x++) {
+				if (state->extra_key[x] == left) {
+					idx = state->extra_idx[x];
+					break;
 				}
 			}
 		}
-		const bool     exc = idx >= ds;  // rd.hpp:138-142
-		const uint32_t m   = __ballot_sync(FULL, exc);
-		if (t == r) { rowmask = m; }
 		on_index(r, idx);
+		myexc |= (uint32_t)(idx >= ds) << r;                   // rd.hpp:138-142
 		a.left_nib[r >> 3] |= (idx & lmask) << (4 * (r & 7));  // FFOR masks the stored index to left_bw bits
 	}
-	a.rowmask = rowmask;
-	a.cnt     = __reduce_add_sync(FULL, (uint32_t)__popc(rowmask));
-	a.bw      = rbw;
-	a.e       = lbw;
-	a.f       = ds;
-	a.base    = 0;
+	a.myexc = myexc;
+	a.cnt   = __reduce_add_sync(FULL, (uint32_t)__popc(myexc));
+	a.bw    = rbw;
+	a.e     = lbw;
+	a.f     = ds;
+	a.base  = 0;
+	a.fill  = 0;
 }
 
 // ---- FFOR bit packer (write side of SURVEY.md appendix A.1; src/fastlanes_generated_ffor.cpp:7788-7999) ----------
@@ -238,46 +262,70 @@ struct BitSink {
 	}
 };
 
-// pack a thread's 32 rows of 64-bit-lane values ((payload - base) & mask) into the verbatim block image `blk`
-__device__ __forceinline__ void pack_rows(const uint64_t (&payload)[32], uint64_t base, uint32_t bw, int t, uint8_t* blk) {
+// 64-bit lanes.  Thread (lane, half) produces 32-bit words j = half*bw .. half*bw + bw - 1 of its lane's stream;
+// 64-bit word w of lane l lives at element 16*w + l of the block, so consecutive (even, odd) words are paired in a
+// register and stored as one 64-bit element — 16 lanes x 8 bytes = one full 128-byte line per half-warp.  When bw is odd
+// the word shared by the two halves is completed with one shuffle.  exception slots take `fill` (encoder.hpp:393).
+__device__ __forceinline__ void pack_rows(const uint64_t* __restrict__ tile, uint32_t myexc, uint64_t fill, uint64_t base,
+                                          uint32_t bw, int t, uint8_t* __restrict__ dst) {
 	if (bw == 0) { return; }  // ffor bw=0 writes nothing (src/fastlanes_generated_ffor.cpp:4)
 	const int      lane = t & 15, half = t >> 4;
 	const uint64_t mask = low_mask<uint64_t>(bw);
-	uint32_t*      w32  = reinterpret_cast<uint32_t*>(blk);
-	uint32_t       j    = half * bw;  // 32-bit word index inside the lane's stream
+	uint64_t*      d64  = reinterpret_cast<uint64_t*>(dst);
+	uint32_t       j    = half * bw;
+	uint32_t       even = 0, head = 0;
+	bool           have_even = false;
 	auto           emit = [&](uint32_t w) {
-        w32[32 * (j >> 1) + 2 * lane + (j & 1)] = w;  // 64-bit word (j>>1) of lane `lane` lives at element 16*(j>>1)+lane
+        if (have_even) {
+            d64[16 * (j >> 1) + lane] = (uint64_t)even | ((uint64_t)w << 32);
+            have_even                 = false;
+        } else if (j & 1) {
+            head = w;  // only the first word of half 1 when bw is odd
+        } else {
+            even      = w;
+            have_even = true;
+        }
         j++;
 	};
 	BitSink        sink;
 	const uint32_t n_lo = bw < 32 ? bw : 32, n_hi = bw - n_lo;
-#pragma unroll
+#pragma unroll 4
 	for (int r = 0; r < 32; r++) {
-		const uint64_t d = (payload[r] - base) & mask;
+		uint64_t v = tile[r * 32 + t];
+		if ((myexc >> r) & 1u) { v = fill; }
+		const uint64_t d = (v - base) & mask;
 		sink.push((uint32_t)d, n_lo, emit);
 		if (n_hi) { sink.push((uint32_t)(d >> 32), n_hi, emit); }
 	}
+	if (bw & 1u) {  // half 0 is left with its last (even) word, half 1 with its first (odd) word: same 64-bit element
+		const uint32_t other = __shfl_xor_sync(FULL, half ? head : even, 16);
+		if (half) { d64[16 * ((bw - 1) >> 1) + lane] = (uint64_t)other | ((uint64_t)head << 32); }
+	}
 }
-__device__ __forceinline__ void pack_rows(const uint32_t (&payload)[32], uint32_t base, uint32_t bw, int t, uint8_t* blk) {
+// 32-bit lanes: word j of lane t at element 32*j + t — every store instruction writes one full 128-byte line
+__device__ __forceinline__ void pack_rows(const uint32_t* __restrict__ tile, uint32_t myexc, uint32_t fill, uint32_t base,
+                                          uint32_t bw, int t, uint8_t* __restrict__ dst) {
 	if (bw == 0) { return; }
 	const uint32_t mask = low_mask<uint32_t>(bw);
-	uint32_t*      w32  = reinterpret_cast<uint32_t*>(blk);
+	uint32_t*      d32  = reinterpret_cast<uint32_t*>(dst);
 	uint32_t       j    = 0;
 	auto           emit = [&](uint32_t w) {
-        w32[32 * j + t] = w;
+        d32[32 * j + t] = w;
         j++;
 	};
 	BitSink sink;
-#pragma unroll
+#pragma unroll 4
 	for (int r = 0; r < 32; r++) {
-		sink.push((payload[r] - base) & mask, bw, emit);
+		uint32_t v = tile[r * 32 + t];
+		if ((myexc >> r) & 1u) { v = fill; }
+		sink.push((v - base) & mask, bw, emit);
 	}
 }
 
 __device__ __forceinline__ uint32_t nib(const uint32_t (&n)[4], int r) { return (n[r >> 3] >> (4 * (r & 7))) & 0xFu; }
 
 // pack the ALP_RD dictionary indices on 16-bit lanes (64 lanes x 16 rows): value v = 64*row16 + lane16
-__device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_t lbw, int t, uint16_t* blk, double /*tag*/) {
+__device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_t lbw, int t, uint16_t* __restrict__ blk, double /*tag*/) {
 	// thread (lane, half) holds values 16*(32*half + r) + lane: lane16 = lane + 16*(r&3), row16 = 8*half + (r>>2)
 	const int lane = t & 15, half = t >> 4;
 #pragma unroll
@@ -296,7 +344,7 @@ __device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_
 		}
 	}
 }
-__device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_t lbw, int t, uint16_t* blk, float /*tag*/) {
+__device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_t lbw, int t, uint16_t* __restrict__ blk, float /*tag*/) {
 	// thread t holds values 32*r + t: lane16 = t + 32*(r&1), row16 = r>>1 — two complete 16-row streams
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
@@ -314,9 +362,10 @@ __device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_
 // ---- exception emission in position order (encoder.hpp:390-397 / rd.hpp:138-142) ------------------------------------
 // value_of(p) returns what is stored for position p (the original value for ALP, the left part for ALP_RD).
 template <typename PT, typename ValueOf, typename Store>
-__device__ __forceinline__ void emit_exceptions(uint32_t rowmask, int t, ValueOf&& value_of, Store&& store) {
-	uint32_t rows = __ballot_sync(FULL, rowmask != 0);
-	if (rows == 0) { return; }
+__device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&& value_of, Store&& store) {
+	if (!__any_sync(FULL, myexc != 0)) { return; }
+	const uint32_t rowmask = transpose32(myexc, t);  // lane r: ballot of "is exception" over row r
+	uint32_t       rows    = __ballot_sync(FULL, rowmask != 0);
 	if (sizeof(PT) == 8) {
 		const int lane = t & 15, half = t >> 4;
 		uint32_t  tot_lo, tot_hi;
@@ -351,10 +400,17 @@ __device__ __forceinline__ void emit_exceptions(uint32_t rowmask, int t, ValueOf
 	}
 }
 
-// ---- decoupled look-back over thread blocks ---------------------------------------------------------------------------
-// status word: [63:62] flag (0 empty, 1 block aggregate, 2 inclusive prefix) | [61:32] packed size in 128-byte units |
-// [31:0] exception slots
-constexpr uint64_t LB_AGG = 1ull << 62, LB_PRE = 2ull << 62, LB_VAL = (1ull << 62) - 1;
+// ---- placement: in-order prefix sums over thread blocks ---------------------------------------------------------------
+// Every block publishes its aggregate (packed 128-byte units << 32 | exception slots) and then waits for its exclusive
+// prefix.  The prefixes are produced by ONE scanner warp — the last warp of the block that drew ticket 0 turns into it
+// once its own vector is written — which walks the aggregates in ticket order, 128 per step (one 32-byte sector per
+// lane), and publishes the running sums.  The scanner advances 128 blocks per L2 round trip, several times faster than
+// blocks are produced, so a block waits about one round trip after its slowest predecessor has published.  (A classic
+// decoupled look-back with a 32-wide window per round trip cannot keep up here: ~450 blocks are in flight and the prefix
+// frontier would advance only 32 blocks per round trip.)  Tickets are drawn when a block starts, so every predecessor
+// of a waiting block is already resident: no deadlock.
+// status word: [63] valid | [61:32] packed size in 128-byte units | [31:0] exception slots
+constexpr uint64_t SCAN_VALID = 1ull << 63, SCAN_VAL = (1ull << 62) - 1;
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
 	uint64_t v;
@@ -371,31 +427,41 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
 	}
 	return v;
 }
-// called by one full warp of block `bid`; returns the exclusive prefix (packed units << 32 | exceptions)
-__device__ __forceinline__ uint64_t lookback(uint64_t* status, uint32_t bid, uint64_t aggregate, int t) {
-	if (bid == 0) {
-		if (t == 0) { st_volatile_u64(&status[0], LB_PRE | aggregate); }
-		return 0;
-	}
-	if (t == 0) { st_volatile_u64(&status[bid], LB_AGG | aggregate); }
-	uint64_t excl = 0;
-	int64_t  look = (int64_t)bid - 1;
-	for (;;) {
-		const int64_t idx = look - t;
-		uint64_t      val = LB_PRE;  // before block 0: an inclusive prefix of zero
-		if (idx >= 0) { val = ld_volatile_u64(&status[idx]); }
-		if (__any_sync(FULL, (val >> 62) == 0)) { continue; }  // someone has not published yet: look again
-		const uint32_t pre = __ballot_sync(FULL, (val >> 62) == 2);
-		if (pre) {
-			const int first = __ffs(pre) - 1;  // nearest predecessor with an inclusive prefix
-			excl += warp_sum_u64(t <= first ? (val & LB_VAL) : 0);
-			break;
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
+	const uint32_t lo = __shfl_up_sync(FULL, (uint32_t)v, d), hi = __shfl_up_sync(FULL, (uint32_t)(v >> 32), d);
+	return ((uint64_t)hi << 32) | lo;
+}
+// run by one warp: aggregates[0..n_blocks) -> prefixes[0..n_blocks) (exclusive), in order
+__device__ __forceinline__ void scan_blocks(const uint64_t* aggregates, uint64_t* prefixes, uint32_t n_blocks, int t) {
+	uint64_t running = 0;
+	for (uint32_t base = 0; base < n_blocks; base += 128) {
+		uint64_t v[4];
+		bool     ok;
+		do {
+			ok = true;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t idx = base + 4 * t + k;
+				v[k]               = idx < n_blocks ? ld_volatile_u64(&aggregates[idx]) : SCAN_VALID;
+				ok                 = ok && (v[k] & SCAN_VALID);
+			}
+		} while (!__all_sync(FULL, ok));
+		const uint64_t mine = (v[0] & SCAN_VAL) + (v[1] & SCAN_VAL) + (v[2] & SCAN_VAL) + (v[3] & SCAN_VAL);
+		uint64_t       incl = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint64_t o = shfl_up_u64(incl, d);
+			if (t >= d) { incl += o; }
 		}
-		excl += warp_sum_u64(val & LB_VAL);
-		look -= 32;
+		uint64_t excl = running + incl - mine;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t idx = base + 4 * t + k;
+			if (idx < n_blocks) { st_volatile_u64(&prefixes[idx], SCAN_VALID | excl); }
+			excl += v[k] & SCAN_VAL;
+		}
+		running += shfl_u64(incl, 31);
 	}
-	if (t == 0) { st_volatile_u64(&status[bid], LB_PRE | (excl + aggregate)); }
-	return excl;
 }
 
 struct ColOut {
@@ -408,14 +474,15 @@ struct ColOut {
 	uint64_t*         totals;
 };
 
-// workspace layout: [0] ticket counter, [1] reserved, [2..] one status word per thread block
+// workspace layout: [0] ticket counter, [1] reserved, [2 .. 2+n_blocks) block aggregates, [2+n_blocks .. 2+2*n_blocks)
+// exclusive prefixes.
+// Shared memory: one [32][32] tile of UT per warp (8 KiB f64 / 4 KiB f32).
 template <typename PT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
                                                             const alpb200_rg_state* __restrict__ states, ColOut col,
                                                             uint64_t* workspace) {
 	using T  = Traits<PT>;
 	using UT = typename T::UT;
-	constexpr uint32_t STAGE = (sizeof(PT) == 8 ? 66u : 35u) * 128u;  // widest block: 63+3 bits (f64 RD) / 32+3 bits
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t s_bid;
 	__shared__ uint32_t s_units[WARPS], s_cnt[WARPS];
@@ -427,13 +494,11 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 	const uint32_t bid    = s_bid;
 	const uint64_t v      = (uint64_t)bid * WARPS + warp;
 	const bool     active = v < n_vectors;
-	uint8_t*       blk    = smem + (size_t)warp * STAGE;
+	UT*            tile   = reinterpret_cast<UT*>(smem) + (size_t)warp * VEC;
 
 	Analysis<PT> a;
-	a.cnt = 0;
-	a.bw = a.e = a.f = 0;
-	a.rowmask        = 0;
-	a.base           = 0;
+	a.cnt = a.bw = a.e = a.f = a.myexc = 0;
+	a.base = a.fill = 0;
 	StateRegs st;
 	st.scheme                      = ALPB200_SCHEME_INVALID;
 	const PT*               in_vec = in + v * (uint64_t)VEC;
@@ -442,10 +507,10 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 	if (active) {
 		st = load_state(state);
 		if (st.scheme == ALPB200_SCHEME_ALP_RD) {
-			analyze_rd<PT>(in_vec, state, st, t, a, [](int, uint32_t) {});
+			analyze_rd<PT>(in_vec, state, st, t, tile, a, [](int, uint32_t) {});
 			units = a.bw + a.e;
 		} else {
-			analyze_alp<PT>(in_vec, st, t, a);
+			analyze_alp<PT>(in_vec, st, t, tile, a);
 			units = a.bw;
 		}
 	}
@@ -459,7 +524,16 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 		if (t < WARPS) { mine = ((uint64_t)s_units[t] << 32) | s_cnt[t]; }
 		const uint64_t agg  = warp_sum_u64(mine);
 		const uint32_t wide = __reduce_max_sync(FULL, (uint32_t)(mine >> 32));
-		const uint64_t excl = lookback(workspace + 2, bid, agg, t);
+		uint64_t* aggregates = workspace + 2;
+		uint64_t* prefixes   = aggregates + gridDim.x;
+		uint64_t  excl       = 0;
+		if (t == 0) {
+			st_volatile_u64(&aggregates[bid], SCAN_VALID | agg);
+			if (bid != 0) {
+				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) {}
+				excl &= SCAN_VAL;
+			}
+		}
 		if (t == 0) {
 			s_excl = excl;
 			atomicMax(reinterpret_cast<unsigned long long*>(&col.totals[3]), (unsigned long long)wide * 128ull);
@@ -471,7 +545,11 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 		}
 	}
 	__syncthreads();
-	if (!active) { return; }
+	const bool scanner = bid == 0 && warp == WARPS - 1;  // this warp produces every block's prefix once its own work is done
+	if (!active) {
+		if (scanner) { scan_blocks(workspace + 2, workspace + 2 + gridDim.x, gridDim.x, t); }
+		return;
+	}
 	uint64_t units_off = s_excl >> 32, exc_off = s_excl & 0xFFFFFFFFull;
 	for (int w = 0; w < warp; w++) {
 		units_off += s_units[w];
@@ -480,27 +558,21 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 	const uint32_t bytes = units * 128u;
 	if (units_off * 128ull + bytes > col.packed_capacity || exc_off + a.cnt > col.exc_capacity) {
 		if (t == 0) { atomicExch(reinterpret_cast<unsigned long long*>(&col.totals[2]), 1ull); }
+		if (scanner) { scan_blocks(workspace + 2, workspace + 2 + gridDim.x, gridDim.x, t); }
 		return;
 	}
 
-	// ---- pack into the shared-memory image of the block, then one bulk store ----
-	const bool rd = st.scheme == ALPB200_SCHEME_ALP_RD;
-	pack_rows(a.payload, (UT)a.base, a.bw, t, blk);
-	if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(blk + 128u * a.bw), PT()); }
-	if (bytes) {
-		fence_proxy_async_smem();
-		__syncwarp();
-		if (t == 0) {
-			bulk_s2g(col.packed + units_off * 128ull, blk, bytes);
-			bulk_commit();
-		}
-	}
+	// ---- FFOR from the tile straight into the column ----
+	const bool rd  = st.scheme == ALPB200_SCHEME_ALP_RD;
+	uint8_t*   dst = col.packed + units_off * 128ull;
+	pack_rows(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t, dst);  // ALP_RD exceptions concern the left parts only
+	if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(dst + 128u * a.bw), PT()); }
 	// ---- exceptions, in position order ----
-	UT*       ev  = static_cast<UT*>(col.exc_val) + exc_off;
-	uint16_t* ep  = col.exc_pos + exc_off;
+	UT*            ev  = static_cast<UT*>(col.exc_val) + exc_off;
+	uint16_t*      ep  = col.exc_pos + exc_off;
 	const uint32_t rbw = a.bw;
 	emit_exceptions<PT>(
-	    a.rowmask, t,
+	    a.myexc, t,
 	    [&](uint32_t p) -> UT {
 		    const UT bits = T::bits(in_vec[p]);
 		    return rd ? (UT)(bits >> rbw) : bits;
@@ -522,10 +594,13 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 		rb.y = (uint32_t)exc_off;
 		rb.z = a.cnt | (st.scheme << 16) | (a.bw << 24);
 		rb.w = a.e | (a.f << 8);
-		uint4* dst = reinterpret_cast<uint4*>(col.meta + v);
-		dst[0]     = ra;
-		dst[1]     = rb;
-		if (bytes) { bulk_wait_read_all(); }  // the stage must outlive the bulk store's read of it
+		uint4* out = reinterpret_cast<uint4*>(col.meta + v);
+		out[0]     = ra;
+		out[1]     = rb;
+	}
+	if (scanner) {
+		__syncwarp();
+		scan_blocks(workspace + 2, workspace + 2 + gridDim.x, gridDim.x, t);
 	}
 }
 

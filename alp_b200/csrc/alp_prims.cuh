@@ -14,17 +14,18 @@ __global__ void __launch_bounds__(32) prim_encode_kernel(const PT* __restrict__ 
                                                          typename Traits<PT>::UT* __restrict__ exc, uint16_t* __restrict__ pos,
                                                          uint16_t* __restrict__ cnt, typename Traits<PT>::UT* __restrict__ enc,
                                                          uint8_t* __restrict__ ef) {
-	using UT    = typename Traits<PT>::UT;
-	const int t = threadIdx.x;
-	StateRegs st = load_state(state);
+	using UT = typename Traits<PT>::UT;
+	__shared__ __align__(128) UT tile[VEC];
+	const int    t  = threadIdx.x;
+	StateRegs    st = load_state(state);
 	Analysis<PT> a;
-	analyze_alp<PT>(in, st, t, a);
-#pragma unroll
+	analyze_alp<PT>(in, st, t, tile, a);
+	__syncwarp();
 	for (int r = 0; r < 32; r++) {
-		enc[Map<PT>::index(t, r)] = a.payload[r];
+		enc[Map<PT>::index(t, r)] = ((a.myexc >> r) & 1u) ? (UT)a.fill : tile[r * 32 + t];  // encoder.hpp:393
 	}
 	emit_exceptions<PT>(
-	    a.rowmask, t, [&](uint32_t p) -> UT { return Traits<PT>::bits(in[p]); },
+	    a.myexc, t, [&](uint32_t p) -> UT { return Traits<PT>::bits(in[p]); },
 	    [&](uint32_t rank, uint32_t p, UT val) {
 		    exc[rank] = val;
 		    pos[rank] = (uint16_t)p;
@@ -61,20 +62,13 @@ template <typename PT>
 __global__ void __launch_bounds__(32) prim_ffor_kernel(const typename Traits<PT>::UT* __restrict__ in, uint8_t* __restrict__ out,
                                                        uint32_t bw, typename Traits<PT>::UT base) {
 	using UT = typename Traits<PT>::UT;
-	__shared__ __align__(128) uint8_t blk[64 * 128 + STAGE_PAD];
+	__shared__ __align__(128) UT tile[VEC];
 	const int t = threadIdx.x;
-	UT        payload[32];
-#pragma unroll
 	for (int r = 0; r < 32; r++) {
-		payload[r] = in[Map<PT>::index(t, r)];
+		tile[r * 32 + t] = in[Map<PT>::index(t, r)];
 	}
-	pack_rows(payload, base, bw, t, blk);
 	__syncwarp();
-	const uint4* src = reinterpret_cast<const uint4*>(blk);
-	uint4*       dst = reinterpret_cast<uint4*>(out);
-	for (uint32_t i = t; i < bw * 8u; i += 32) {
-		dst[i] = src[i];
-	}
+	pack_rows(tile, 0u, (UT)0, base, bw, t, out);
 }
 
 // ffor / unffor on 16-bit lanes (ffor.hpp:9): 64 lanes x 16 rows, value v = 64*row + lane.  Plain loops.
@@ -181,18 +175,19 @@ __global__ void __launch_bounds__(32) prim_rd_encode_kernel(const PT* __restrict
                                                             uint16_t* __restrict__ exc, uint16_t* __restrict__ pos,
                                                             uint16_t* __restrict__ cnt, typename Traits<PT>::UT* __restrict__ right,
                                                             uint16_t* __restrict__ left) {
-	using UT    = typename Traits<PT>::UT;
-	const int t = threadIdx.x;
-	StateRegs st = load_state(state);
+	using UT = typename Traits<PT>::UT;
+	__shared__ __align__(128) UT tile[VEC];
+	const int    t  = threadIdx.x;
+	StateRegs    st = load_state(state);
 	Analysis<PT> a;
-	analyze_rd<PT>(in, state, st, t, a, [&](int r, uint32_t idx) { left[Map<PT>::index(t, r)] = (uint16_t)idx; });
-#pragma unroll
+	analyze_rd<PT>(in, state, st, t, tile, a, [&](int r, uint32_t idx) { left[Map<PT>::index(t, r)] = (uint16_t)idx; });
+	__syncwarp();
 	for (int r = 0; r < 32; r++) {
-		right[Map<PT>::index(t, r)] = a.payload[r];
+		right[Map<PT>::index(t, r)] = tile[r * 32 + t];
 	}
 	const uint32_t rbw = a.bw;
 	emit_exceptions<PT>(
-	    a.rowmask, t, [&](uint32_t p) -> UT { return (UT)(Traits<PT>::bits(in[p]) >> rbw); },
+	    a.myexc, t, [&](uint32_t p) -> UT { return (UT)(Traits<PT>::bits(in[p]) >> rbw); },
 	    [&](uint32_t rank, uint32_t p, UT val) {
 		    exc[rank] = (uint16_t)val;
 		    pos[rank] = (uint16_t)p;
