@@ -4,7 +4,8 @@ import os
 
 from . import _abi
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libalp_b200.so")
+# ALPB200_LIB lets a developer load an experimental build of the same library (tools/decode_probe.py)
+LIB_PATH = os.environ.get("ALPB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libalp_b200.so")
 
 _c = ctypes
 _P = ctypes.c_void_p

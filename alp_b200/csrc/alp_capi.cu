@@ -45,7 +45,12 @@ constexpr int ENC_WARPS = 8;
 struct DeviceInfo {
 	int sms = 0;
 	int smem_optin = 0;
+	// work-distribution counters of the decode kernel: one slot per launch, handed out round-robin, zeroed on the
+	// launch's stream right before the kernel (the library allocates this once per device; nothing on the hot path)
+	unsigned long long* counters = nullptr;
+	uint32_t            next_counter = 0;
 };
+constexpr uint32_t N_COUNTERS = 4096;
 DeviceInfo g_dev[64];
 std::mutex g_dev_mutex;
 
@@ -57,7 +62,9 @@ int device_info(DeviceInfo& out) {
 	if (g_dev[dev].sms == 0) {
 		CUDA_TRY(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
 		CUDA_TRY(cudaDeviceGetAttribute(&g_dev[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+		CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&g_dev[dev].counters), N_COUNTERS * sizeof(unsigned long long)));
 	}
+	g_dev[dev].next_counter = (g_dev[dev].next_counter + 1) % N_COUNTERS;
 	out = g_dev[dev];
 	return ALPB200_OK;
 }
@@ -74,8 +81,10 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
 	uint32_t       block  = col->max_block_bytes ? (uint32_t)std::min<uint64_t>(col->max_block_bytes, widest) : widest;
 	const uint32_t stage  = ((block + 127u) & ~127u) + STAGE_PAD;
-	const size_t   smem   = (size_t)DEC_WARPS * 2 * stage + DEC_WARPS * 2 * sizeof(uint64_t);
-	auto           kern   = decode_kernel<PT, DEC_WARPS>;
+	// narrow blocks: decode into a shared-memory tile and bulk-store it; wide blocks (ALP_RD, bw > 32): direct line stores
+	const bool   tile = stage <= 4096 + STAGE_PAD;
+	const size_t smem = (size_t)DEC_WARPS * ((tile ? VEC * sizeof(PT) : 0) + 2 * stage) + DEC_WARPS * 2 * sizeof(uint64_t);
+	auto         kern = tile ? decode_kernel<PT, DEC_WARPS, true> : decode_kernel<PT, DEC_WARPS, false>;
 	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_WARPS * 32, smem));
@@ -83,7 +92,9 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
 	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
 	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
-	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_out, stage);
+	unsigned long long* counter = di.counters + di.next_counter;
+	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
+	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_out, stage, counter);
 	CUDA_TRY(cudaGetLastError());
 	return ALPB200_OK;
 }

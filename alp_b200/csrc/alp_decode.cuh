@@ -17,8 +17,26 @@
 #pragma once
 
 #include "alp_device.cuh"
+#include "alp_ffor.cuh"
+
+// build-time knobs (tools/decode_probe.py builds variants to compare them on the GPU)
+#ifndef ALPB200_DEC_MINBLOCKS
+#define ALPB200_DEC_MINBLOCKS 2  // resident CTAs per SM the register allocation is limited for
+#endif
+#ifndef ALPB200_DEC_STREAMING_STORES
+#define ALPB200_DEC_STREAMING_STORES 0  // 1: st.global.cs for the decoded values (written once, never re-read)
+#endif
 
 namespace alpb200 {
+
+template <typename V>
+__device__ __forceinline__ void store_out(V* p, V v) {
+#if ALPB200_DEC_STREAMING_STORES
+	__stcs(p, v);
+#else
+	*p = v;
+#endif
+}
 
 struct ColView {
 	const alpb200_vec_meta* meta;
@@ -53,72 +71,103 @@ __device__ __forceinline__ MetaRegs load_meta(const alpb200_vec_meta* m) {
 }
 
 // ---- ALP, 64-bit lanes -------------------------------------------------------------------------------------------
+// One `switch (bw)` per vector (warp-uniform) into a template instance whose shifts, masks and offsets are constants.
 __device__ __forceinline__ void decode_alp_vector(const uint8_t* stage, const MetaRegs& m, double* __restrict__ out_vec, int t) {
 	using T             = Traits<double>;
-	const uint32_t bw   = m.bw();
 	const int      lane = t & 15, half = t >> 4;
 	const int64_t  fact = T::fact10(m.f());
 	const double   frac = T::frac10(m.e());
 	const uint64_t base = m.base();
 	double*        o    = out_vec + 512 * half + lane;  // value index 16*(32*half + r) + lane
-	if (bw == 0) {  // unffor bw=0 broadcasts the base (src/fastlanes_generated_unffor.cpp:4-22)
-		const double v = decode_value<double>((int64_t)base, fact, frac);
-#pragma unroll 8
-		for (int r = 0; r < 32; r++) {
-			o[16 * r] = v;
-		}
-		return;
-	}
-	const uint64_t* blk  = reinterpret_cast<const uint64_t*>(stage);
-	const uint64_t  mask = low_mask<uint64_t>(bw);
-	uint32_t        bit  = 32u * bw * half;
-#pragma unroll 4
-	for (int r = 0; r < 32; r++, bit += bw) {
-		const uint64_t d = extract64(blk, lane, bit, mask);
-		o[16 * r]        = decode_value<double>((int64_t)(d + base), fact, frac);  // src/falp.cpp:1049-1056
-	}
+	dispatch_width<0, 64>(m.bw(), [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		unpack64_rows<BW>(stage, lane, half, [&](int r, uint32_t lo, uint32_t hi) {
+			const uint64_t d = BW <= 32 ? (uint64_t)lo : ((uint64_t)hi << 32) | lo;
+			store_out(&o[16 * r], decode_value<double>((int64_t)(d + base), fact, frac));  // src/falp.cpp:1049-1056
+		});
+	});
 }
 
 // ---- ALP, 32-bit lanes -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void decode_alp_vector(const uint8_t* stage, const MetaRegs& m, float* __restrict__ out_vec, int t) {
 	using T             = Traits<float>;
-	const uint32_t bw   = m.bw();
 	const int32_t  fact = T::fact10(m.f());
 	const float    frac = T::frac10(m.e());
 	const uint32_t base = m.a.x;
 	float*         o    = out_vec + t;  // value index 32*r + lane
-	if (bw == 0) {
-		const float v = decode_value<float>((int32_t)base, fact, frac);
-#pragma unroll 8
-		for (int r = 0; r < 32; r++) {
-			o[32 * r] = v;
-		}
-		return;
-	}
-	const uint32_t* blk  = reinterpret_cast<const uint32_t*>(stage);
-	const uint32_t  mask = low_mask<uint32_t>(bw);
-	uint32_t        bit  = 0;
-#pragma unroll 8
-	for (int r = 0; r < 32; r++, bit += bw) {
-		const uint32_t d = extract32(blk, t, bit, mask);
-		o[32 * r]        = decode_value<float>((int32_t)(d + base), fact, frac);
-	}
+	dispatch_width<0, 32>(m.bw(), [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		unpack32_rows<BW>(stage, t, [&](int r, uint32_t d) { store_out(&o[32 * r], decode_value<float>((int32_t)(d + base), fact, frac)); });
+	});
 }
 
-// ---- ALP exception patch (decoder.hpp:141-149) ----------------------------------------------------------------
+// ---- exceptions ------------------------------------------------------------------------------------------------------
+// The first 32 exceptions of a vector (one per lane) are fetched one vector ahead, so that the patch never waits for
+// DRAM; longer runs fall back to a loop.
+template <typename UT>
+struct ExcRegs {
+	uint32_t pos;
+	UT       val;
+};
+template <typename UT>
+__device__ __forceinline__ ExcRegs<UT> load_exceptions(const ColView& col, const MetaRegs& m, int t) {
+	ExcRegs<UT> x;
+	x.pos = 0;
+	x.val = 0;
+	if ((uint32_t)t < m.exc_cnt()) {
+		x.pos = __ldg(col.exc_pos + m.exc_off() + t);
+		x.val = __ldg(static_cast<const UT*>(col.exc_val) + m.exc_off() + t);
+	}
+	return x;
+}
+// exceptions 32.. of a vector: pull their cache lines towards the SM one vector ahead (lane i takes line i)
+__device__ __forceinline__ void prefetch_exception_tail(const ColView& col, const MetaRegs& m, int t, uint32_t value_bytes) {
+	const uint32_t cnt = m.exc_cnt();
+	if (cnt <= 32) { return; }
+	const uint64_t first = (uint64_t)m.exc_off() + 32, last = (uint64_t)m.exc_off() + cnt - 1;
+	const char*    v0    = static_cast<const char*>(col.exc_val) + ((first * value_bytes) & ~127ull);
+	const char*    v1    = static_cast<const char*>(col.exc_val) + last * value_bytes;
+	const char*    p0    = reinterpret_cast<const char*>(col.exc_pos) + ((first * 2) & ~127ull);
+	const char*    p1    = reinterpret_cast<const char*>(col.exc_pos) + last * 2;
+	for (const char* a = v0 + 128 * t; a <= v1; a += 128 * 32) {
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+	}
+	if (p0 + 128 * t <= p1) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 128 * t)); }
+}
+
+// ALP exception patch (decoder.hpp:141-149)
 template <typename PT>
-__device__ __forceinline__ void patch_alp(const ColView& col, const MetaRegs& m, PT* __restrict__ out_vec, int t) {
-	const uint32_t  cnt = m.exc_cnt();
-	const PT*       ev  = static_cast<const PT*>(col.exc_val) + m.exc_off();
-	const uint16_t* ep  = col.exc_pos + m.exc_off();
-	for (uint32_t i = t; i < cnt; i += 32) {
-		out_vec[ep[i]] = ev[i];
+__device__ __forceinline__ void patch_alp(const ColView& col, const MetaRegs& m, const ExcRegs<typename Traits<PT>::UT>& x,
+                                          PT* __restrict__ out_vec, int t) {
+	using UT           = typename Traits<PT>::UT;
+	const uint32_t cnt = m.exc_cnt();
+	UT*            ov  = reinterpret_cast<UT*>(out_vec);
+	if ((uint32_t)t < cnt) { ov[x.pos] = x.val; }
+	if (cnt > 32) {
+		const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
+		const uint16_t* ep = col.exc_pos + m.exc_off();
+		for (uint32_t i = t + 32; i < cnt; i += 96) {  // three independent (position, value) loads in flight per lane
+			const uint32_t i1 = i + 32, i2 = i + 64;
+			uint32_t       p0 = ep[i], p1 = 0, p2 = 0;
+			UT             v0 = ev[i], v1 = 0, v2 = 0;
+			if (i1 < cnt) {
+				p1 = ep[i1];
+				v1 = ev[i1];
+			}
+			if (i2 < cnt) {
+				p2 = ep[i2];
+				v2 = ev[i2];
+			}
+			ov[p0] = v0;
+			if (i1 < cnt) { ov[p1] = v1; }
+			if (i2 < cnt) { ov[p2] = v2; }
+		}
 	}
 }
 
 // ---- ALP_RD (rd.hpp:152-178): right parts on T-bit lanes, dictionary indices on 16-bit lanes -----------------------
 __device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const ColView& col, const MetaRegs& m,
-                                                 double* __restrict__ out_vec, int t) {
+                                                 const ExcRegs<uint64_t>& x, double* __restrict__ out_vec, int t) {
 	const uint32_t  rbw = m.bw(), lbw = m.e();
 	const int       lane = t & 15, half = t >> 4;
 	const uint64_t* rblk  = reinterpret_cast<const uint64_t*>(stage);
@@ -126,65 +175,89 @@ __device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const Col
 	const uint64_t  rmask = low_mask<uint64_t>(rbw);
 	const uint32_t  lmask = (1u << lbw) - 1;
 	uint64_t*       o     = reinterpret_cast<uint64_t*>(out_vec) + 512 * half + lane;
-	uint32_t        bit   = 32u * rbw * half;
-#pragma unroll 4
-	for (int r = 0; r < 32; r++, bit += rbw) {
-		const uint64_t right = extract64(rblk, lane, bit, rmask);
-		const uint32_t v     = 16u * (32u * half + r) + lane;  // 16-bit-lane coordinates of the same value
-		const uint32_t idx   = extract16(lblk, v & 63, (v >> 6) * lbw, lmask);
-		o[16 * r]            = ((uint64_t)dict_lookup(m.a, idx) << rbw) | right;
-	}
+	dispatch_width<48, 63>(rbw < 48 ? 48u : rbw, [&](auto W) {  // right_bit_width = 64 - cut, cut in 1..16 (rd.hpp:95)
+		constexpr int BW = decltype(W)::value;
+		unpack64_rows<BW>(stage, lane, half, [&](int r, uint32_t lo, uint32_t hi) {
+			const uint64_t right = ((uint64_t)hi << 32) | lo;
+			const uint32_t v     = 16u * (32u * half + r) + lane;  // 16-bit-lane coordinates of the same value
+			const uint32_t idx   = extract16(lblk, v & 63, (v >> 6) * lbw, lmask);
+			store_out(&o[16 * r], ((uint64_t)dict_lookup(m.a, idx) << BW) | right);
+		});
+	});
 	__syncwarp();
 	// exceptions: the true left part replaces the dictionary entry (rd.hpp:172-177)
-	const uint32_t  cnt = m.exc_cnt();
-	const uint64_t* ev  = static_cast<const uint64_t*>(col.exc_val) + m.exc_off();
-	const uint16_t* ep  = col.exc_pos + m.exc_off();
-	uint64_t*       ov  = reinterpret_cast<uint64_t*>(out_vec);
-	for (uint32_t i = t; i < cnt; i += 32) {
-		const uint32_t p     = ep[i];
-		const uint64_t right = extract64(rblk, p & 15, (p >> 4) * rbw, rmask);
-		ov[p]                = ((ev[i] & 0xFFFFu) << rbw) | right;
+	const uint32_t cnt = m.exc_cnt();
+	uint64_t*      ov  = reinterpret_cast<uint64_t*>(out_vec);
+	if ((uint32_t)t < cnt) {
+		const uint64_t right = extract64(rblk, x.pos & 15, (x.pos >> 4) * rbw, rmask);
+		ov[x.pos]            = ((x.val & 0xFFFFu) << rbw) | right;
+	}
+	if (cnt > 32) {
+		const uint64_t* ev = static_cast<const uint64_t*>(col.exc_val) + m.exc_off();
+		const uint16_t* ep = col.exc_pos + m.exc_off();
+		for (uint32_t i = t + 32; i < cnt; i += 32) {
+			const uint32_t p     = ep[i];
+			const uint64_t right = extract64(rblk, p & 15, (p >> 4) * rbw, rmask);
+			ov[p]                = ((ev[i] & 0xFFFFu) << rbw) | right;
+		}
 	}
 }
 
 __device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const ColView& col, const MetaRegs& m,
-                                                 float* __restrict__ out_vec, int t) {
+                                                 const ExcRegs<uint32_t>& x, float* __restrict__ out_vec, int t) {
 	const uint32_t  rbw = m.bw(), lbw = m.e();
 	const uint32_t* rblk  = reinterpret_cast<const uint32_t*>(stage);
 	const uint16_t* lblk  = reinterpret_cast<const uint16_t*>(stage + 128u * rbw);
 	const uint32_t  rmask = low_mask<uint32_t>(rbw);
 	const uint32_t  lmask = (1u << lbw) - 1;
 	uint32_t*       o     = reinterpret_cast<uint32_t*>(out_vec) + t;
-	uint32_t        bit   = 0;
-#pragma unroll 4
-	for (int r = 0; r < 32; r++, bit += rbw) {
-		const uint32_t right = extract32(rblk, t, bit, rmask);
-		const uint32_t v     = 32u * r + t;
-		const uint32_t idx   = extract16(lblk, v & 63, (v >> 6) * lbw, lmask);
-		o[32 * r]            = (dict_lookup(m.a, idx) << rbw) | right;
-	}
+	dispatch_width<16, 31>(rbw < 16 ? 16u : rbw, [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		unpack32_rows<BW>(stage, t, [&](int r, uint32_t right) {
+			const uint32_t v   = 32u * r + t;
+			const uint32_t idx = extract16(lblk, v & 63, (v >> 6) * lbw, lmask);
+			store_out(&o[32 * r], (dict_lookup(m.a, idx) << BW) | right);
+		});
+	});
 	__syncwarp();
-	const uint32_t  cnt = m.exc_cnt();
-	const uint32_t* ev  = static_cast<const uint32_t*>(col.exc_val) + m.exc_off();
-	const uint16_t* ep  = col.exc_pos + m.exc_off();
-	uint32_t*       ov  = reinterpret_cast<uint32_t*>(out_vec);
-	for (uint32_t i = t; i < cnt; i += 32) {
-		const uint32_t p     = ep[i];
-		const uint32_t right = extract32(rblk, p & 31, (p >> 5) * rbw, rmask);
-		ov[p]                = ((ev[i] & 0xFFFFu) << rbw) | right;
+	const uint32_t cnt = m.exc_cnt();
+	uint32_t*      ov  = reinterpret_cast<uint32_t*>(out_vec);
+	if ((uint32_t)t < cnt) {
+		const uint32_t right = extract32(rblk, x.pos & 31, (x.pos >> 5) * rbw, rmask);
+		ov[x.pos]            = ((x.val & 0xFFFFu) << rbw) | right;
+	}
+	if (cnt > 32) {
+		const uint32_t* ev = static_cast<const uint32_t*>(col.exc_val) + m.exc_off();
+		const uint16_t* ep = col.exc_pos + m.exc_off();
+		for (uint32_t i = t + 32; i < cnt; i += 32) {
+			const uint32_t p     = ep[i];
+			const uint32_t right = extract32(rblk, p & 31, (p >> 5) * rbw, rmask);
+			ov[p]                = ((ev[i] & 0xFFFFu) << rbw) | right;
+		}
 	}
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
 // Persistent warps: warp g of the grid decodes vectors g, g + G, g + 2G, ...  Each warp owns two shared-memory
-// stages of `stage_bytes` and two mbarriers.
-template <typename PT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) decode_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
-                                                            PT* __restrict__ out, uint32_t stage_bytes) {
+// stages of `stage_bytes` and two mbarriers.  Software pipeline per warp: records are read two vectors ahead, the
+// packed block and the first 32 exceptions one vector ahead.
+// OUT_TILE: decode into a per-warp shared-memory tile, patch exceptions there, and write the vector with ONE contiguous
+// 8 / 4 KiB bulk-async store (TMA 1-D) — measured +4..7 % on write-heavy ALP columns over per-row line stores because
+// DRAM sees dense sequential writes.  Without it (wide blocks, e.g. ALP_RD, where the tile would halve occupancy) the
+// warp stores full 128-byte lines directly and patches exceptions afterwards while the lines are still in L2.
+template <typename PT, int WARPS, bool OUT_TILE>
+__global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
+                                                               PT* __restrict__ out, uint32_t stage_bytes,
+                                                               unsigned long long* __restrict__ counter) {
+	using UT = typename Traits<PT>::UT;
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
-	uint8_t*  stage = smem + (size_t)warp * 2 * stage_bytes;
-	uint64_t* bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * 2 * stage_bytes) + 2 * warp;
+	// per warp: [decoded vector tile (OUT_TILE) | packed stage 0 | packed stage 1]
+	constexpr uint32_t TILE  = OUT_TILE ? VEC * sizeof(PT) : 0;
+	uint8_t*           mine  = smem + (size_t)warp * (TILE + 2 * stage_bytes);
+	PT*                tile  = reinterpret_cast<PT*>(mine);
+	uint8_t*           stage = mine + TILE;
+	uint64_t*          bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * (TILE + 2 * stage_bytes)) + 2 * warp;
 	if (t == 0) {
 		mbar_init(&bars[0], 1);
 		mbar_init(&bars[1], 1);
@@ -192,8 +265,27 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(ColView col, uint64_
 	}
 	__syncwarp();
 
-	const uint64_t stride = (uint64_t)gridDim.x * WARPS;
-	uint64_t       v      = (uint64_t)blockIdx.x * WARPS + warp;
+	// Dynamic work distribution: a warp draws chunks of CHUNK consecutive vectors from a global counter (the next chunk
+	// is requested while a few vectors of the current one are left, so the atomic's latency never stalls the pipeline).
+	// SMs differ in their distance to memory; with a static split the fast ones idle at the end (ncu: SM active 85 %).
+	constexpr uint32_t CHUNK = 16, REFILL_AT = 6;
+	auto draw = [&]() -> uint64_t {
+		unsigned long long b = 0;
+		if (t == 0) { b = atomicAdd(counter, (unsigned long long)CHUNK); }
+		return shfl_u64(b, 0);
+	};
+	uint64_t chunk_base = draw(), next_base = 0;
+	uint32_t chunk_used = 0;
+	auto     take       = [&]() -> uint64_t {
+        if (chunk_used == CHUNK) {
+            chunk_base = next_base;
+            chunk_used = 0;
+        }
+        const uint64_t idx = chunk_base + chunk_used++;
+        if (chunk_used == CHUNK - REFILL_AT) { next_base = draw(); }
+        return idx;
+	};
+	uint64_t v = take(), v_next = take();
 	if (v >= n_vectors) { return; }
 	const alpb200_vec_meta* meta = col.meta + first_vector;
 
@@ -206,36 +298,63 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(ColView col, uint64_
 	};
 
 	MetaRegs cur = load_meta(meta + v);
-	bool     has_next = v + stride < n_vectors;
+	bool     has_next = v_next < n_vectors;
 	MetaRegs nxt      = cur;
-	if (has_next) { nxt = load_meta(meta + v + stride); }
+	if (has_next) { nxt = load_meta(meta + v_next); }
 	issue(cur, 0);
-	uint32_t phase = 0;  // bit s: parity the next wait on stage s must see
+	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
+	uint32_t    phase = 0;  // bit s: parity the next wait on stage s must see
 	for (int s = 0;; s ^= 1) {
-		if (has_next) { issue(nxt, s ^ 1); }  // stage s^1 was drained one iteration ago (see __syncwarp below)
-		const bool has_nn = v + 2 * stride < n_vectors;
-		MetaRegs   nn     = nxt;
-		if (has_nn) { nn = load_meta(meta + v + 2 * stride); }
+		ExcRegs<UT> xnxt = xcur;
+		if (has_next) {
+			issue(nxt, s ^ 1);  // stage s^1 was drained one iteration ago (see __syncwarp below)
+			xnxt = load_exceptions<UT>(col, nxt, t);
+			prefetch_exception_tail(col, nxt, t, sizeof(UT));
+		}
+		const uint64_t v_nn   = has_next ? take() : v_next;
+		const bool     has_nn = has_next && v_nn < n_vectors;
+		MetaRegs       nn     = nxt;
+		if (has_nn) { nn = load_meta(meta + v_nn); }
 
-		PT*            out_vec = out + v * (uint64_t)VEC;
-		const uint8_t* stg     = stage + (size_t)s * stage_bytes;
+		const uint8_t* stg = stage + (size_t)s * stage_bytes;
 		if (cur.block_bytes() != 0) {
 			mbar_wait(&bars[s], (phase >> s) & 1u);
 			phase ^= 1u << s;
 		}
+		PT* out_vec = out + v * (uint64_t)VEC;
+		if constexpr (OUT_TILE) {
+			// the previous vector's bulk store must have finished READING the tile before it is overwritten
+			if (t == 0) { bulk_wait_read_all(); }
+			__syncwarp();
+			out_vec = tile;
+		}
 		if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			decode_alp_vector(stg, cur, out_vec, t);
 			__syncwarp();  // orders the patch stores after the lane-interleaved main stores
-			patch_alp<PT>(col, cur, out_vec, t);
+			patch_alp<PT>(col, cur, xcur, out_vec, t);
 		} else {
-			decode_rd_vector(stg, col, cur, out_vec, t);
+			decode_rd_vector(stg, col, cur, xcur, out_vec, t);
+		}
+		if constexpr (OUT_TILE) {
+			fence_proxy_async_smem();  // generic-proxy writes to the tile -> visible to the bulk-copy engine
 		}
 		__syncwarp();  // every lane is done reading stage s before lane 0 refills it two iterations from now
+		if constexpr (OUT_TILE) {
+			if (t == 0) {
+				bulk_s2g(out + v * (uint64_t)VEC, tile, TILE);  // one contiguous 8 / 4 KiB write per vector (TMA 1-D)
+				bulk_commit();
+			}
+		}
 		if (!has_next) { break; }
 		cur      = nxt;
 		nxt      = nn;
+		xcur     = xnxt;
 		has_next = has_nn;
-		v += stride;
+		v        = v_next;
+		v_next   = v_nn;
+	}
+	if constexpr (OUT_TILE) {
+		if (t == 0) { bulk_wait_all(); }  // the last store must be complete before the tile's CTA goes away
 	}
 }
 

@@ -245,6 +245,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // FastLanes interleaved layout, read side (src/fastlanes_generated_unffor.cpp:6389-6500).

