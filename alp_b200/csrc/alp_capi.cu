@@ -116,7 +116,7 @@ int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, 
 	CUDA_TRY(cudaMemsetAsync(ws, 0, encode_workspace_bytes(n), s));
 	CUDA_TRY(cudaMemsetAsync(col->totals, 0, 4 * sizeof(uint64_t), s));
 	if (n == 0) { return ALPB200_OK; }
-	constexpr size_t smem = (size_t)ENC_WARPS * VEC * sizeof(PT);  // one [32][32] tile per warp
+	constexpr size_t smem = (size_t)ENC_WARPS * EncodeCfg<PT>::SMEM_PER_WARP;  // f64: one tile per warp; f32: one stage per warp
 	auto             kern = encode_kernel<PT, ENC_WARPS>;
 	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	ColOut         out {col->meta, col->packed, col->packed_capacity, col->exc_val, col->exc_pos, col->exc_capacity, col->totals};

@@ -127,6 +127,59 @@ __device__ __forceinline__ void choose_exponent_factor(PT xs, const StateRegs& s
 	f_out = best_f;
 }
 
+// ---- value access policies -------------------------------------------------------------------------------------------
+// The analysis and packing code reads row r of the thread's 32 rows through an IO policy with a compile-time row
+// number.  GlobalIO streams the vector from global memory in double-buffered batches of 8 rows (every warp load
+// instruction covers full 128-byte lines); TileIO works on a shared-memory copy of the vector (value order) and can
+// store the encoded integers back — used by the single-vector primitives, which must return them.
+template <typename PT>
+struct GlobalIO {
+	using UT = typename Traits<PT>::UT;
+	static constexpr int B = 8;
+	const PT* in;
+	int       t;
+	UT        cur[B], nxt[B];
+	__device__ __forceinline__ GlobalIO(const PT* in_vec, int lane_id) : in(in_vec), t(lane_id) {
+#pragma unroll
+		for (int i = 0; i < B; i++) {
+			nxt[i] = Traits<PT>::bits(in[Map<PT>::index(t, i)]);
+		}
+	}
+	template <int R>
+	__device__ __forceinline__ UT load(std::integral_constant<int, R>) {
+		if constexpr (R % B == 0) {
+#pragma unroll
+			for (int i = 0; i < B; i++) {
+				cur[i] = nxt[i];
+			}
+			if constexpr (R + B < 32) {
+#pragma unroll
+				for (int i = 0; i < B; i++) {
+					nxt[i] = Traits<PT>::bits(in[Map<PT>::index(t, R + B + i)]);
+				}
+			}
+		}
+		return cur[R % B];
+	}
+	template <int R>
+	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT) {}
+};
+template <typename PT>
+struct TileIO {
+	using UT = typename Traits<PT>::UT;
+	UT* tile;
+	int t;
+	__device__ __forceinline__ TileIO(UT* tile_, int lane_id) : tile(tile_), t(lane_id) {}
+	template <int R>
+	__device__ __forceinline__ UT load(std::integral_constant<int, R>) {
+		return tile[Map<PT>::index(t, R)];
+	}
+	template <int R>
+	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT v) {
+		tile[Map<PT>::index(t, R)] = v;
+	}
+};
+
 // ---- ALP analysis: encoder.hpp:307-400 + :109-120 ------------------------------------------------------------------
 // Exception test.  The reference pre-replaces special values (double: -0.0; float: NaN, ±Inf, -0.0; encoder.hpp:326-338)
 // by ENCODING_UPPER_LIMIT, which never round-trips, and then flags `decoded != value` (:374-379).  Comparing the BIT
@@ -137,33 +190,33 @@ __device__ __forceinline__ void choose_exponent_factor(PT xs, const StateRegs& s
 // min/max of the non-exceptions (analyze_ffor, encoder.hpp:109-120; exception slots hold `fill`, itself a
 // non-exception).  64-bit integers have no native min/max (2 ISETP + 2 SEL each), so the common case — all high
 // words equal, e.g. every encoded integer in [0, 2^32) — tracks unsigned min/max of the low words plus AND/OR of the
-// high words (4 predicated instructions per value) and falls back to a second pass over the tile otherwise.
-template <typename PT>
-__device__ __forceinline__ void analyze_alp(const StateRegs& st, int t, typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a) {
+// high words, branch-free, and falls back to a second pass over the input otherwise.
+template <typename PT, typename IO>
+__device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const StateRegs& st, int t, IO& io, Analysis<PT>& a) {
 	using T  = Traits<PT>;
 	using UT = typename T::UT;
 	using ST = typename T::ST;
-	// the tile holds the input vector in value order (tile[v] = bits of value v); it is overwritten in place with the
-	// encoded integers.  A half-warp touches 128 contiguous bytes per access: conflict-free.
 	int e = st.exp_of(0), f = st.fac_of(0);
-	if (st.k > 1) { choose_exponent_factor<PT>(T::from_bits(tile[32 * t]), st, e, f); }  // encoder.hpp:409-412
+	if (st.k > 1) { choose_exponent_factor<PT>(in_vec[32 * t], st, e, f); }  // encoder.hpp:409-412
 	const PT ex = T::exp10(e), frf = T::frac10(f), fre = T::frac10(e);
 	const ST fa = T::fact10(f);
-	__syncwarp();  // every lane has its sample before the tile is overwritten
 
 	uint32_t myexc = 0;
 	uint32_t lo_min = 0xFFFFFFFFu, lo_max = 0, hi_and = 0xFFFFFFFFu, hi_or = 0;  // f64
 	ST       mn = T::ST_MAX, mx = T::ST_MIN;                                       // f32
+	ST       first = 0;       // encoded integer of this thread's first non-exception
+	uint32_t unseen = 0xFFFFFFFFu;  // all-ones until the thread has met a non-exception
 	static_for<0, 32>([&](auto R) {
-		constexpr int r   = decltype(R)::value;
-		UT*           slot = tile + Map<PT>::index(t, r);
-		const UT      xb  = *slot;
-		const ST      enc = encode_value<PT, false>(T::from_bits(xb), ex, frf);  // encoder.hpp:345
-		const PT      dec = decode_value<PT>(enc, fa, fre);                       // :347
-		const bool    exc = T::bits(dec) != xb;
-		*slot             = (UT)enc;
-		const uint32_t em = exc ? 0xFFFFFFFFu : 0u;  // branch-free: exceptions are neutral for min / max / and / or
+		constexpr int  r   = decltype(R)::value;
+		const UT       xb  = io.load(R);
+		const ST       enc = encode_value<PT, false>(T::from_bits(xb), ex, frf);  // encoder.hpp:345
+		const PT       dec = decode_value<PT>(enc, fa, fre);                       // :347
+		const bool     exc = T::bits(dec) != xb;
+		const uint32_t em  = exc ? 0xFFFFFFFFu : 0u;  // branch-free: exceptions are neutral for min / max / and / or
+		io.store(R, (UT)enc);
 		myexc |= em & (1u << r);
+		first = (unseen & ~em) ? enc : first;
+		unseen &= em;
 		if constexpr (sizeof(PT) == 8) {
 			const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
 			lo_min = min(lo_min, lo | em);
@@ -182,19 +235,19 @@ __device__ __forceinline__ void analyze_alp(const StateRegs& st, int t, typename
 	if (~myexc) { cand = (uint32_t)Map<PT>::index(t, __ffs((int)~myexc) - 1); }
 	cand   = __reduce_min_sync(FULL, cand);
 	a.fill = 0;
-	__syncwarp();
 	if (cand != 0xFFFFu) {
-		a.fill = (ST)tile[cand];
+		const int owner = Map<PT>::thread_of((int)cand);
 		if constexpr (sizeof(PT) == 8) {
+			a.fill = (ST)shfl_u64((uint64_t)first, owner);
 			hi_and = __reduce_and_sync(FULL, hi_and);
 			hi_or  = __reduce_or_sync(FULL, hi_or);
 			if (hi_and == hi_or) {  // one common high word: order is decided by the low words
 				mn = (ST)(((uint64_t)hi_or << 32) | __reduce_min_sync(FULL, lo_min));
 				mx = (ST)(((uint64_t)hi_or << 32) | __reduce_max_sync(FULL, lo_max));
-			} else {  // wide range: full 64-bit pass over the tile
-#pragma unroll 8
+			} else {  // wide range: full 64-bit pass, re-encoding from the input
+#pragma unroll 4
 				for (int r = 0; r < 32; r++) {
-					const ST v = (ST)tile[Map<PT>::index(t, r)];
+					const ST v = encode_value<PT, false>(in_vec[Map<PT>::index(t, r)], ex, frf);
 					if (!((myexc >> r) & 1u)) {
 						mn = v < mn ? v : mn;
 						mx = v > mx ? v : mx;
@@ -204,8 +257,9 @@ __device__ __forceinline__ void analyze_alp(const StateRegs& st, int t, typename
 				mx = warp_max<ST>(mx);
 			}
 		} else {
-			mn = warp_min<ST>(mn);
-			mx = warp_max<ST>(mx);
+			a.fill = (ST)__shfl_sync(FULL, (int)first, owner);
+			mn     = warp_min<ST>(mn);
+			mx     = warp_max<ST>(mx);
 		}
 	} else {
 		mn = mx = 0;
@@ -218,22 +272,21 @@ __device__ __forceinline__ void analyze_alp(const StateRegs& st, int t, typename
 
 // ---- ALP_RD analysis: rd.hpp:109-147 --------------------------------------------------------------------------------
 // on_index(r, idx) reports the unmasked dictionary index of row r (what rd.hpp:136 stores before FFOR masks it).
-template <typename PT, typename OnIndex>
-__device__ __forceinline__ void analyze_rd(const alpb200_rg_state* state, const StateRegs& st, int t,
-                                           typename Traits<PT>::UT* __restrict__ tile, Analysis<PT>& a, OnIndex&& on_index) {
+template <typename PT, typename IO, typename OnIndex>
+__device__ __forceinline__ void analyze_rd(const alpb200_rg_state* state, const StateRegs& st, int t, IO& io, Analysis<PT>& a,
+                                           OnIndex&& on_index) {
 	using T              = Traits<PT>;
 	using UT             = typename T::UT;
 	const uint32_t rbw   = st.right_bw(), lbw = st.left_bw(), ds = st.dict_size();
 	const UT       rmask = low_mask<UT>(rbw);
 	const uint32_t lmask = (1u << lbw) - 1;
 	uint32_t       myexc = 0;
-	a.left_nib[0] = a.left_nib[1] = a.left_nib[2] = a.left_nib[3] = 0;
-#pragma unroll 8
-	for (int r = 0; r < 32; r++) {
-		UT*            slot = tile + Map<PT>::index(t, r);
-		const UT       bits = *slot;
+	uint32_t       nib0 = 0, nib1 = 0, nib2 = 0, nib3 = 0;
+	static_for<0, 32>([&](auto R) {
+		constexpr int  r    = decltype(R)::value;
+		const UT       bits = io.load(R);
 		const uint32_t left = (uint32_t)(bits >> rbw);
-		*slot               = bits & rmask;
+		io.store(R, bits & rmask);
 		uint32_t idx = ds;  // rd.hpp:129-131: a left part nobody has seen gets the smallest non-dictionary index
 		bool     hit = false;
 #pragma unroll
@@ -252,16 +305,29 @@ __device__ __forceinline__ void analyze_rd(const alpb200_rg_state* state, const 
 			}
 		}
 		on_index(r, idx);
-		myexc |= (uint32_t)(idx >= ds) << r;                   // rd.hpp:138-142
-		a.left_nib[r >> 3] |= (idx & lmask) << (4 * (r & 7));  // FFOR masks the stored index to left_bw bits
-	}
-	a.myexc = myexc;
-	a.cnt   = __reduce_add_sync(FULL, (uint32_t)__popc(myexc));
-	a.bw    = rbw;
-	a.e     = lbw;
-	a.f     = ds;
-	a.base  = 0;
-	a.fill  = 0;
+		myexc |= (uint32_t)(idx >= ds) << r;  // rd.hpp:138-142
+		const uint32_t n = (idx & lmask) << (4 * (r & 7));  // FFOR masks the stored index to left_bw bits
+		if constexpr (r < 8) {
+			nib0 |= n;
+		} else if constexpr (r < 16) {
+			nib1 |= n;
+		} else if constexpr (r < 24) {
+			nib2 |= n;
+		} else {
+			nib3 |= n;
+		}
+	});
+	a.left_nib[0] = nib0;
+	a.left_nib[1] = nib1;
+	a.left_nib[2] = nib2;
+	a.left_nib[3] = nib3;
+	a.myexc       = myexc;
+	a.cnt         = __reduce_add_sync(FULL, (uint32_t)__popc(myexc));
+	a.bw          = rbw;
+	a.e           = lbw;
+	a.f           = ds;
+	a.base        = 0;
+	a.fill        = 0;
 }
 
 // ---- FFOR bit packer (write side of SURVEY.md appendix A.1; src/fastlanes_generated_ffor.cpp:7788-7999) ----------
@@ -275,8 +341,9 @@ __device__ __forceinline__ void pack_rows(const uint64_t* __restrict__ tile, uin
 	dispatch_width<0, 64>(bw, [&](auto W) {
 		constexpr int BW = decltype(W)::value;
 		if constexpr (BW > 0) {  // ffor bw=0 writes nothing (src/fastlanes_generated_ffor.cpp:4)
-			pack64_rows<BW>(lane, half, reinterpret_cast<uint64_t*>(dst), [&](int r, uint32_t& lo, uint32_t& hi) {
-				uint64_t v = tile[Map<double>::index(t, r)];
+			pack64_rows<BW>(lane, half, reinterpret_cast<uint64_t*>(dst), [&](auto R, uint32_t& lo, uint32_t& hi) {
+				constexpr int r = decltype(R)::value;
+				uint64_t      v = tile[Map<double>::index(t, r)];
 				if ((myexc >> r) & 1u) { v = fill; }
 				const uint64_t d = v - base;  // masked to BW bits by the packer
 				lo               = (uint32_t)d;
@@ -291,8 +358,33 @@ __device__ __forceinline__ void pack_rows(const uint32_t* __restrict__ tile, uin
 	dispatch_width<0, 32>(bw, [&](auto W) {
 		constexpr int BW = decltype(W)::value;
 		if constexpr (BW > 0) {
-			pack32_rows<BW>(t, reinterpret_cast<uint32_t*>(dst), [&](int r) -> uint32_t {
-				uint32_t v = tile[Map<float>::index(t, r)];
+			pack32_rows<BW>(t, reinterpret_cast<uint32_t*>(dst), [&](auto R) -> uint32_t {
+				constexpr int r = decltype(R)::value;
+				uint32_t      v = tile[Map<float>::index(t, r)];
+				if ((myexc >> r) & 1u) { v = fill; }
+				return v - base;
+			});
+		}
+	});
+}
+
+// ---- second pass of the batched encoder: FFOR straight from the input ------------------------------------------------
+// Re-reads the vector (L2-resident: this warp streamed it a moment ago), re-encodes it with the chosen (e,f) — no
+// decode/compare, the exception bitmap is known — and packs.  dst may be shared or global memory.
+// (not inlined: keeps the 33 width instances out of the kernel body)
+__device__ __noinline__ void pack_from_input(const float* __restrict__ in_vec, uint32_t bw, uint32_t e, uint32_t f, uint32_t base,
+                                             uint32_t fill, uint32_t myexc, bool rd, int t, uint8_t* __restrict__ dst) {
+	using T = Traits<float>;
+	const float ex = T::exp10(rd ? 0 : e), frf = T::frac10(rd ? 0 : f);
+	if (rd) { myexc = 0; }
+	dispatch_width<0, 32>(bw, [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		if constexpr (BW > 0) {
+			GlobalIO<float> io(in_vec, t);
+			pack32_rows<BW>(t, reinterpret_cast<uint32_t*>(dst), [&](auto R) -> uint32_t {
+				constexpr int  r    = decltype(R)::value;
+				const uint32_t bits = io.load(R);
+				uint32_t       v    = rd ? bits : (uint32_t)encode_value<float, false>(T::from_bits(bits), ex, frf);
 				if ((myexc >> r) & 1u) { v = fill; }
 				return v - base;
 			});
@@ -471,13 +563,39 @@ struct ColOut {
 
 // workspace layout: [0] ticket counter, [1] reserved, [2 .. 2+n_blocks) block aggregates, [2+n_blocks .. 2+2*n_blocks)
 // exclusive prefixes.
-// Shared memory: one [32][32] tile of UT per warp (8 KiB f64 / 4 KiB f32).
+//
+// One CTA = WARPS vectors, one warp each.  Two strategies, chosen per value type from measurements on B200:
+//
+//  * ONE PASS (f64): the vector arrives in a per-warp shared-memory tile with one bulk-async copy (TMA 1-D), is encoded
+//    in place, and is packed from the tile once the CTA's output offsets are known.  The 8 KiB tile limits residency to
+//    3 CTAs per SM, but each value is touched once (a second encode pass costs ~850 warp-instructions per f64 vector).
+//  * TWO PASSES (f32): pass 1 analyses without staging anything; after the CTA's aggregate is published, pass 2 re-reads
+//    the vector (L2), re-encodes it and FFORs into a 4.4 KiB per-warp stage while the scanner works out the offsets;
+//    the stage then leaves with one bulk-async store.  Small footprint -> 4 CTAs per SM, and the wait is overlapped.
+template <typename PT>
+struct EncodeCfg;
+template <>
+struct EncodeCfg<double> {
+	static constexpr bool     TWO_PASS       = false;
+	static constexpr uint32_t SMEM_PER_WARP  = VEC * sizeof(double);  // the tile
+	static constexpr uint32_t STAGE_UNITS    = 0;
+	static constexpr int      MIN_BLOCKS     = 3;
+};
+template <>
+struct EncodeCfg<float> {
+	static constexpr bool     TWO_PASS       = true;
+	static constexpr uint32_t STAGE_UNITS    = 35;  // every f32 block fits: 32 bits, or ALP_RD 31 + 3
+	static constexpr uint32_t SMEM_PER_WARP  = STAGE_UNITS * 128u;
+	static constexpr int      MIN_BLOCKS     = 4;
+};
+
 template <typename PT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 3) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
-                                                            const alpb200_rg_state* __restrict__ states, ColOut col,
-                                                            uint64_t* workspace) {
-	using T  = Traits<PT>;
-	using UT = typename T::UT;
+__global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
+                                                                                    const alpb200_rg_state* __restrict__ states,
+                                                                                    ColOut col, uint64_t* workspace) {
+	using T   = Traits<PT>;
+	using UT  = typename T::UT;
+	using Cfg = EncodeCfg<PT>;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t s_bid;
 	__shared__ uint32_t s_units[WARPS], s_cnt[WARPS];
@@ -490,7 +608,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) encode_kernel(const PT* __restr
 	const uint32_t bid    = s_bid;
 	const uint64_t v      = (uint64_t)bid * WARPS + warp;
 	const bool     active = v < n_vectors;
-	UT*            tile   = reinterpret_cast<UT*>(smem) + (size_t)warp * VEC;
+	uint8_t*       mine   = smem + (size_t)warp * Cfg::SMEM_PER_WARP;  // f64: the tile;  f32: the packed-block stage
+	UT*            tile   = reinterpret_cast<UT*>(mine);
 
 	Analysis<PT> a;
 	a.cnt = a.bw = a.e = a.f = a.myexc = 0;
@@ -500,59 +619,84 @@ __global__ void __launch_bounds__(WARPS * 32, 3) encode_kernel(const PT* __restr
 	const PT*               in_vec = in + v * (uint64_t)VEC;
 	const alpb200_rg_state* state  = states + (active ? v / ALPB200_ROWGROUP_VECTORS : 0);
 	uint32_t                units  = 0;
+	bool                    rd     = false;
 	if (active) {
-		// the whole input vector (8 / 4 KiB, contiguous) arrives in the tile with one bulk-async copy (TMA 1-D)
-		if (t == 0) {
-			mbar_init(&s_bar[warp], 1);
-			fence_mbar_init();
-			mbar_arrive_expect_tx(&s_bar[warp], VEC * sizeof(PT));
-			bulk_g2s(tile, in_vec, VEC * sizeof(PT), &s_bar[warp]);
+		if constexpr (!Cfg::TWO_PASS) {
+			// the whole input vector (contiguous) arrives in the tile with one bulk-async copy (TMA 1-D)
+			if (t == 0) {
+				mbar_init(&s_bar[warp], 1);
+				fence_mbar_init();
+				mbar_arrive_expect_tx(&s_bar[warp], VEC * sizeof(PT));
+				bulk_g2s(tile, in_vec, VEC * sizeof(PT), &s_bar[warp]);
+			}
 		}
 		st = load_state(state);
-		__syncwarp();
-		mbar_wait(&s_bar[warp], 0);
-		if (st.scheme == ALPB200_SCHEME_ALP_RD) {
-			analyze_rd<PT>(state, st, t, tile, a, [](int, uint32_t) {});
-			units = a.bw + a.e;
+		rd = st.scheme == ALPB200_SCHEME_ALP_RD;
+		if constexpr (!Cfg::TWO_PASS) {
+			__syncwarp();
+			mbar_wait(&s_bar[warp], 0);
+			TileIO<PT> io(tile, t);
+			if (rd) {
+				analyze_rd<PT>(state, st, t, io, a, [](int, uint32_t) {});
+			} else {
+				analyze_alp<PT>(in_vec, st, t, io, a);
+			}
 		} else {
-			analyze_alp<PT>(st, t, tile, a);
-			units = a.bw;
+			GlobalIO<PT> io(in_vec, t);
+			if (rd) {
+				analyze_rd<PT>(state, st, t, io, a, [](int, uint32_t) {});
+			} else {
+				analyze_alp<PT>(in_vec, st, t, io, a);
+			}
 		}
+		units = rd ? a.bw + a.e : a.bw;
 	}
 	if (t == 0) {
 		s_units[warp] = units;
 		s_cnt[warp]   = a.cnt;
 	}
 	__syncthreads();
+	uint64_t* aggregates = workspace + 2;
+	uint64_t* prefixes   = aggregates + gridDim.x;
+	uint64_t  agg        = 0;
 	if (warp == 0) {
-		uint64_t mine = 0;
-		if (t < WARPS) { mine = ((uint64_t)s_units[t] << 32) | s_cnt[t]; }
-		const uint64_t agg  = warp_sum_u64(mine);
-		const uint32_t wide = __reduce_max_sync(FULL, (uint32_t)(mine >> 32));
-		uint64_t* aggregates = workspace + 2;
-		uint64_t* prefixes   = aggregates + gridDim.x;
-		uint64_t  excl       = 0;
+		uint64_t mine_agg = 0;
+		if (t < WARPS) { mine_agg = ((uint64_t)s_units[t] << 32) | s_cnt[t]; }
+		agg                 = warp_sum_u64(mine_agg);
+		const uint32_t wide = __reduce_max_sync(FULL, (uint32_t)(mine_agg >> 32));
 		if (t == 0) {
 			st_volatile_u64(&aggregates[bid], SCAN_VALID | agg);
-			if (bid != 0) {
-				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) {}
-				excl &= SCAN_VAL;
-			}
-		}
-		if (t == 0) {
-			s_excl = excl;
 			atomicMax(reinterpret_cast<unsigned long long*>(&col.totals[3]), (unsigned long long)wide * 128ull);
-			if ((uint64_t)(bid + 1) * WARPS >= n_vectors) {  // last block: publish the column totals
-				const uint64_t incl = excl + agg;
-				col.totals[0]       = (incl >> 32) * 128ull;
-				col.totals[1]       = incl & 0xFFFFFFFFull;
-			}
+		}
+	}
+	const uint32_t bytes = units * 128u;
+	if constexpr (Cfg::TWO_PASS) {
+		// pass 2: pack into the stage while the scanner works out this block's offsets
+		if (active) {
+			pack_from_input(in_vec, a.bw, a.e, a.f, (UT)a.base, (UT)a.fill, a.myexc, rd, t, mine);
+			if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(mine + 128u * a.bw), PT()); }
+			fence_proxy_async_smem();  // generic-proxy writes to the stage -> visible to the bulk-copy engine
+		}
+	}
+	if (warp == 0 && t == 0) {
+		// (a self-service look-back over the 128 nearest predecessors was tried here: one L2 round trip instead of
+		// three, but ~450 spinning blocks x 2 KiB per round put ~1 TB/s of extra traffic on L2 and the kernel got slower)
+		uint64_t excl = 0;
+		if (bid != 0) {
+			while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) {}
+			excl &= SCAN_VAL;
+		}
+		s_excl = excl;
+		if ((uint64_t)(bid + 1) * WARPS >= n_vectors) {  // last block: publish the column totals
+			const uint64_t incl = excl + agg;
+			col.totals[0]       = (incl >> 32) * 128ull;
+			col.totals[1]       = incl & 0xFFFFFFFFull;
 		}
 	}
 	__syncthreads();
 	const bool scanner = bid == 0 && warp == WARPS - 1;  // this warp produces every block's prefix once its own work is done
 	if (!active) {
-		if (scanner) { scan_blocks(workspace + 2, workspace + 2 + gridDim.x, gridDim.x, t); }
+		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t); }
 		return;
 	}
 	uint64_t units_off = s_excl >> 32, exc_off = s_excl & 0xFFFFFFFFull;
@@ -560,18 +704,22 @@ __global__ void __launch_bounds__(WARPS * 32, 3) encode_kernel(const PT* __restr
 		units_off += s_units[w];
 		exc_off += s_cnt[w];
 	}
-	const uint32_t bytes = units * 128u;
 	if (units_off * 128ull + bytes > col.packed_capacity || exc_off + a.cnt > col.exc_capacity) {
 		if (t == 0) { atomicExch(reinterpret_cast<unsigned long long*>(&col.totals[2]), 1ull); }
-		if (scanner) { scan_blocks(workspace + 2, workspace + 2 + gridDim.x, gridDim.x, t); }
+		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t); }
 		return;
 	}
-
-	// ---- FFOR from the tile straight into the column ----
-	const bool rd  = st.scheme == ALPB200_SCHEME_ALP_RD;
-	uint8_t*   dst = col.packed + units_off * 128ull;
-	pack_rows(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t, dst);  // ALP_RD exceptions concern the left parts only
-	if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(dst + 128u * a.bw), PT()); }
+	uint8_t* dst = col.packed + units_off * 128ull;
+	if constexpr (Cfg::TWO_PASS) {
+		if (t == 0 && bytes) {
+			bulk_s2g(dst, mine, bytes);  // one contiguous write of the whole block (TMA 1-D)
+			bulk_commit();
+		}
+	} else {
+		// FFOR from the tile straight into the column (ALP_RD exceptions concern the left parts only)
+		pack_rows(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t, dst);
+		if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(dst + 128u * a.bw), PT()); }
+	}
 	// ---- exceptions, in position order ----
 	UT*            ev  = static_cast<UT*>(col.exc_val) + exc_off;
 	uint16_t*      ep  = col.exc_pos + exc_off;
@@ -602,10 +750,13 @@ __global__ void __launch_bounds__(WARPS * 32, 3) encode_kernel(const PT* __restr
 		uint4* out = reinterpret_cast<uint4*>(col.meta + v);
 		out[0]     = ra;
 		out[1]     = rb;
+		if constexpr (Cfg::TWO_PASS) {
+			if (bytes) { bulk_wait_all(); }  // the stage must outlive the bulk store
+		}
 	}
 	if (scanner) {
 		__syncwarp();
-		scan_blocks(workspace + 2, workspace + 2 + gridDim.x, gridDim.x, t);
+		scan_blocks(aggregates, prefixes, gridDim.x, t);
 	}
 }
 

@@ -128,7 +128,7 @@ __device__ __forceinline__ void window_put(uint32_t (&w)[NW], uint32_t x) {
 	}
 }
 
-// 64-bit lanes.  produce(r, lo, hi) yields the (unmasked) field of row r; dst = the block as 64-bit elements.
+// 64-bit lanes.  produce(R, lo, hi) yields the (unmasked) field of row R::value; dst = the block as 64-bit elements.
 // Words are stored as soon as they are complete (all positions are compile-time), so only a few stay live.
 template <int BW, typename Produce>
 __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* __restrict__ dst, Produce&& produce) {
@@ -141,7 +141,7 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* __rest
 	static_for<0, 32>([&](auto R) {
 		constexpr int r = decltype(R)::value;
 		uint32_t      lo, hi;
-		produce(r, lo, hi);
+		produce(R, lo, hi);
 		if constexpr (BW <= 32) {
 			window_put<BW + 1, r * BW, BW>(w, lo);
 		} else {
@@ -167,13 +167,13 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* __rest
 	}
 }
 
-// 32-bit lanes.  produce(r) yields the (unmasked) field of row r; word i of lane t goes to element 32*i + t.
+// 32-bit lanes.  produce(R) yields the (unmasked) field of row R::value; word i of lane t goes to element 32*i + t.
 template <int BW, typename Produce>
 __device__ __forceinline__ void pack32_rows(int t, uint32_t* __restrict__ dst, Produce&& produce) {
 	uint32_t w[BW + 1];
 	static_for<0, 32>([&](auto R) {
 		constexpr int r = decltype(R)::value;
-		window_put<BW + 1, r * BW, BW>(w, produce(r));
+		window_put<BW + 1, r * BW, BW>(w, produce(R));
 		constexpr int done_before = (r * BW) >> 5, done_now = ((r + 1) * BW) >> 5;
 		static_for<done_before, done_now>([&](auto Ic) {
 			constexpr int i = decltype(Ic)::value;

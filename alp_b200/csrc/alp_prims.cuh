@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(32) prim_encode_kernel(const PT* __restrict__ 
 		tile[i] = Traits<PT>::bits(in[i]);
 	}
 	__syncwarp();
-	analyze_alp<PT>(st, t, tile, a);
+	TileIO<PT> io(tile, t);
+	analyze_alp<PT>(in, st, t, io, a);
 	__syncwarp();
 	for (int r = 0; r < 32; r++) {
 		enc[Map<PT>::index(t, r)] = ((a.myexc >> r) & 1u) ? (UT)a.fill : tile[Map<PT>::index(t, r)];  // encoder.hpp:393
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(32) prim_rd_encode_kernel(const PT* __restrict
 		tile[i] = Traits<PT>::bits(in[i]);
 	}
 	__syncwarp();
-	analyze_rd<PT>(state, st, t, tile, a, [&](int r, uint32_t idx) { left[Map<PT>::index(t, r)] = (uint16_t)idx; });
+	TileIO<PT> io(tile, t);
+	analyze_rd<PT>(state, st, t, io, a, [&](int r, uint32_t idx) { left[Map<PT>::index(t, r)] = (uint16_t)idx; });
 	__syncwarp();
 	for (int i = t; i < VEC; i += 32) {
 		right[i] = tile[i];

@@ -341,7 +341,7 @@ def main():
         from oracle import pyoracle
 
         checker = pyoracle.best()
-        n_slice_vec = min(n_vec, (1 << 26) // 1024)
+        n_slice_vec = min(n_vec, (1 << 27) // 1024)  # same bounded sample as `--impl reference`
         sl = col.to_host(0, n_slice_vec)
         threads = host_threads()
         gbps, reps, dt = cpu_decode_baseline(sl, threads, args.cpu_seconds, checker)
