@@ -11,6 +11,7 @@ from .codec import (  # noqa: F401
     DeviceColumn,
     HostCodec,
     decode,
+    decode_sum,
     device_count,
     encode,
     generate,
@@ -24,6 +25,7 @@ __all__ = [
     "HostCodec",
     "LIB_PATH",
     "decode",
+    "decode_sum",
     "device_count",
     "encode",
     "generate",

@@ -172,6 +172,20 @@ def decode(col, first=0, n=None, out=None):
     return out
 
 
+def decode_sum(col, first=0, n=None, out=None):
+    """Fused decode + SUM of vectors [first, first+n): adds into the 1-element float64 CUDA tensor `out` (created
+    zeroed when omitted).  Nothing is written back to HBM; addition order is not fixed."""
+    n = col.n_vectors - first if n is None else n
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float64, device=col.device)
+    _require_cuda(out, "out")
+    st = col.as_struct()
+    with torch.cuda.device(col.device):
+        fn = getattr(lib, "alpb200_decode_sum_" + _sfx(col.value_bytes))
+        check(fn(ctypes.byref(st), first, n, out.data_ptr(), _stream_ptr(col.device)))
+    return out
+
+
 def generate(n_values, kind, device, seed=None, first_index=0, out=None):
     """Synthetic columns of SURVEY.md §8d on the device: kind 2 decimal f64, 3 high-precision f64, 4 mixed f32."""
     seed = {2: 42, 3: 43, 4: 44}[kind] if seed is None else seed

@@ -15,6 +15,7 @@
 #include "alp_encode.cuh"
 #include "alp_init.cuh"
 #include "alp_prims.cuh"
+#include "alp_scan.cuh"
 
 static_assert(sizeof(alpb200_rg_state) == 1196, "alpb200_rg_state layout");
 static_assert(sizeof(alpb200_vec_meta) == 32, "alpb200_vec_meta layout");
@@ -95,6 +96,34 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 	unsigned long long* counter = di.counters + di.next_counter;
 	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
 	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_out, stage, counter);
+	CUDA_TRY(cudaGetLastError());
+	return ALPB200_OK;
+}
+
+template <typename PT>
+int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream) {
+	if (!col || !d_sum) { return fail(ALPB200_EINVAL, "decode_sum: null argument"); }
+	if (first + n > col->n_vectors) { return fail(ALPB200_EINVAL, "decode_sum: vector range outside the column"); }
+	if (n == 0) { return ALPB200_OK; }
+	if (!col->meta || !col->packed) { return fail(ALPB200_EINVAL, "decode_sum: null argument"); }
+	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0) { return fail(ALPB200_EINVAL, "decode_sum: column.packed must be 128-byte aligned"); }
+	DeviceInfo di;
+	if (int rc = device_info(di)) { return rc; }
+	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
+	uint32_t       block  = col->max_block_bytes ? (uint32_t)std::min<uint64_t>(col->max_block_bytes, widest) : widest;
+	const uint32_t stage  = ((block + 127u) & ~127u) + STAGE_PAD;
+	const size_t   smem   = (size_t)DEC_WARPS * 2 * stage + DEC_WARPS * 2 * sizeof(uint64_t);
+	auto           kern   = decode_sum_kernel<PT, DEC_WARPS>;
+	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_WARPS * 32, smem));
+	if (per_sm < 1) { return fail(ALPB200_ECUDA, "decode_sum: kernel does not fit on an SM"); }
+	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
+	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	unsigned long long* counter = di.counters + di.next_counter;
+	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
+	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_sum, stage, counter);
 	CUDA_TRY(cudaGetLastError());
 	return ALPB200_OK;
 }
@@ -566,6 +595,13 @@ int alpb200_decode_f64(const alpb200_column* col, uint64_t first, uint64_t n, do
 }
 int alpb200_decode_f32(const alpb200_column* col, uint64_t first, uint64_t n, float* d_out, void* stream) {
 	return launch_decode<float>(col, first, n, d_out, stream);
+}
+
+int alpb200_decode_sum_f64(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream) {
+	return launch_decode_sum<double>(col, first, n, d_sum, stream);
+}
+int alpb200_decode_sum_f32(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream) {
+	return launch_decode_sum<float>(col, first, n, d_sum, stream);
 }
 
 int alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes) {

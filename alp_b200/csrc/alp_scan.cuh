@@ -1,0 +1,181 @@
+// alp_scan.cuh — fused decode + SUM: the compressed column is decoded in registers and aggregated; nothing is written
+// back.  This is the reference's scan primitive `alp_func` (AVX-512 falp + patch_exceptions into a thread-private
+// 8 KiB buffer) followed by `aggr_plus` (publication/source_code/bench_end_to_end/src/benchmarks/alp/queries/q1.cpp:63-102)
+// as one kernel: the write-bound decode (8 B/value out) becomes a read-bound scan (~bw/8 B/value in).
+//
+// Same machinery as decode_kernel: persistent warps, chunks of vectors drawn from a global counter, packed blocks
+// fetched by bulk-async copies (TMA 1-D) into a double-buffered stage, width-specialised unpack.  Exceptions: the
+// vector is summed with its fill values first, then every exception adds (true value - decoded fill value).  Floating-
+// point addition order is not fixed (per-thread partial sums, warp tree, one atomicAdd per warp).
+#pragma once
+
+#include "alp_decode.cuh"
+#include "alp_encode.cuh"
+
+namespace alpb200 {
+
+// decoded value at position p of an ALP vector, recomputed from the stage (run-time width)
+__device__ __forceinline__ double alp_value_at(const uint8_t* stage, const MetaRegs& m, uint32_t p, double) {
+	using T              = Traits<double>;
+	const uint32_t bw    = m.bw();
+	const uint64_t d     = bw ? extract64(reinterpret_cast<const uint64_t*>(stage), p & 15, (p >> 4) * bw, low_mask<uint64_t>(bw)) : 0;
+	return decode_value<double>((int64_t)(d + m.base()), T::fact10(m.f()), T::frac10(m.e()));
+}
+__device__ __forceinline__ double alp_value_at(const uint8_t* stage, const MetaRegs& m, uint32_t p, float) {
+	using T           = Traits<float>;
+	const uint32_t bw = m.bw();
+	const uint32_t d  = bw ? extract32(reinterpret_cast<const uint32_t*>(stage), p & 31, (p >> 5) * bw, low_mask<uint32_t>(bw)) : 0;
+	return (double)decode_value<float>((int32_t)(d + m.a.x), T::fact10(m.f()), T::frac10(m.e()));
+}
+
+__device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, double) {
+	using T             = Traits<double>;
+	const int64_t  fact = T::fact10(m.f());
+	const double   frac = T::frac10(m.e());
+	const uint64_t base = m.base();
+	double         acc  = 0.0;
+	dispatch_width<0, 64>(m.bw(), [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		unpack64_rows<BW>(stage, t & 15, t >> 4, [&](int, uint32_t lo, uint32_t hi) {
+			const uint64_t d = BW <= 32 ? (uint64_t)lo : ((uint64_t)hi << 32) | lo;
+			acc += decode_value<double>((int64_t)(d + base), fact, frac);
+		});
+	});
+	return acc;
+}
+__device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, float) {
+	using T             = Traits<float>;
+	const int32_t  fact = T::fact10(m.f());
+	const float    frac = T::frac10(m.e());
+	const uint32_t base = m.a.x;
+	double         acc  = 0.0;
+	dispatch_width<0, 32>(m.bw(), [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		unpack32_rows<BW>(stage, t, [&](int, uint32_t d) { acc += (double)decode_value<float>((int32_t)(d + base), fact, frac); });
+	});
+	return acc;
+}
+
+// ALP_RD value at position p: (left << right_bw) | right, left from the dictionary or, for exceptions, given
+template <typename PT>
+__device__ __forceinline__ double rd_value(const uint8_t* stage, const MetaRegs& m, uint32_t p, bool use_left, uint32_t left_part) {
+	using T   = Traits<PT>;
+	using UT  = typename T::UT;
+	const uint32_t rbw = m.bw(), lbw = m.e();
+	UT             right;
+	if (sizeof(PT) == 8) {
+		right = (UT)extract64(reinterpret_cast<const uint64_t*>(stage), p & 15, (p >> 4) * rbw, low_mask<uint64_t>(rbw));
+	} else {
+		right = (UT)extract32(reinterpret_cast<const uint32_t*>(stage), p & 31, (p >> 5) * rbw, low_mask<uint32_t>(rbw));
+	}
+	if (!use_left) {
+		const uint32_t idx = extract16(reinterpret_cast<const uint16_t*>(stage + 128u * rbw), p & 63, (p >> 6) * lbw, (1u << lbw) - 1);
+		left_part          = dict_lookup(m.a, idx);
+	}
+	return (double)T::from_bits(((UT)left_part << rbw) | right);
+}
+
+template <typename PT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) decode_sum_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
+                                                                  double* __restrict__ sum, uint32_t stage_bytes,
+                                                                  unsigned long long* __restrict__ counter) {
+	using UT = typename Traits<PT>::UT;
+	extern __shared__ __align__(128) uint8_t smem[];
+	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	uint8_t*  stage = smem + (size_t)warp * 2 * stage_bytes;
+	uint64_t* bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * 2 * stage_bytes) + 2 * warp;
+	if (t == 0) {
+		mbar_init(&bars[0], 1);
+		mbar_init(&bars[1], 1);
+		fence_mbar_init();
+	}
+	__syncwarp();
+
+	constexpr uint32_t CHUNK = 16, REFILL_AT = 6;
+	auto draw = [&]() -> uint64_t {
+		unsigned long long b = 0;
+		if (t == 0) { b = atomicAdd(counter, (unsigned long long)CHUNK); }
+		return shfl_u64(b, 0);
+	};
+	uint64_t chunk_base = draw(), next_base = 0;
+	uint32_t chunk_used = 0;
+	auto     take       = [&]() -> uint64_t {
+        if (chunk_used == CHUNK) {
+            chunk_base = next_base;
+            chunk_used = 0;
+        }
+        const uint64_t idx = chunk_base + chunk_used++;
+        if (chunk_used == CHUNK - REFILL_AT) { next_base = draw(); }
+        return idx;
+	};
+	uint64_t v = take(), v_next = take();
+	if (v >= n_vectors) { return; }
+	const alpb200_vec_meta* meta = col.meta + first_vector;
+	auto issue = [&](const MetaRegs& m, int s) {
+		const uint32_t bytes = m.block_bytes();
+		if (t == 0 && bytes != 0) {
+			mbar_arrive_expect_tx(&bars[s], bytes);
+			bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
+		}
+	};
+	MetaRegs cur = load_meta(meta + v);
+	bool     has_next = v_next < n_vectors;
+	MetaRegs nxt      = cur;
+	if (has_next) { nxt = load_meta(meta + v_next); }
+	issue(cur, 0);
+	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
+	uint32_t    phase = 0;
+	double      acc   = 0.0;
+	for (int s = 0;; s ^= 1) {
+		ExcRegs<UT> xnxt = xcur;
+		if (has_next) {
+			issue(nxt, s ^ 1);
+			xnxt = load_exceptions<UT>(col, nxt, t);
+			prefetch_exception_tail(col, nxt, t, sizeof(UT));
+		}
+		const uint64_t v_nn   = has_next ? take() : v_next;
+		const bool     has_nn = has_next && v_nn < n_vectors;
+		MetaRegs       nn     = nxt;
+		if (has_nn) { nn = load_meta(meta + v_nn); }
+		const uint8_t* stg = stage + (size_t)s * stage_bytes;
+		if (cur.block_bytes() != 0) {
+			mbar_wait(&bars[s], (phase >> s) & 1u);
+			phase ^= 1u << s;
+		}
+		const uint32_t  cnt = cur.exc_cnt();
+		const UT*       ev  = static_cast<const UT*>(col.exc_val) + cur.exc_off();
+		const uint16_t* ep  = col.exc_pos + cur.exc_off();
+		if (cur.scheme() == ALPB200_SCHEME_ALP) {
+			acc += sum_alp_vector(stg, cur, t, PT());
+			for (uint32_t i = t; i < cnt; i += 32) {  // exception: + true value - decoded fill value
+				const uint32_t p   = i < 32 ? xcur.pos : ep[i];
+				const UT       val = i < 32 ? xcur.val : ev[i];
+				acc += (double)Traits<PT>::from_bits(val) - alp_value_at(stg, cur, p, PT());
+			}
+		} else {
+			for (int r = 0; r < 32; r++) {
+				acc += rd_value<PT>(stg, cur, (uint32_t)Map<PT>::index(t, r), false, 0);
+			}
+			for (uint32_t i = t; i < cnt; i += 32) {
+				const uint32_t p    = i < 32 ? xcur.pos : ep[i];
+				const uint32_t left = (uint32_t)((i < 32 ? xcur.val : ev[i]) & 0xFFFFu);
+				acc += rd_value<PT>(stg, cur, p, true, left) - rd_value<PT>(stg, cur, p, false, 0);
+			}
+		}
+		__syncwarp();
+		if (!has_next) { break; }
+		cur      = nxt;
+		nxt      = nn;
+		xcur     = xnxt;
+		has_next = has_nn;
+		v        = v_next;
+		v_next   = v_nn;
+	}
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1) {
+		acc += __longlong_as_double((long long)shfl_xor_i64((int64_t)__double_as_longlong(acc), m));
+	}
+	if (t == 0) { atomicAdd(sum, acc); }
+}
+
+}  // namespace alpb200

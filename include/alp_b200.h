@@ -157,6 +157,16 @@ int alpb200_decode_f64(const alpb200_column* col, uint64_t first_vector, uint64_
 int alpb200_decode_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, float* d_out,
                        void* stream);
 
+/* Fused decode + SUM (no decoded column is written): *d_sum += sum of the decoded values of vectors
+ * [first_vector, first_vector + n_vectors), accumulated in double.  The caller zeroes *d_sum.  Floating-point
+ * addition order is not fixed (per-thread partial sums, one atomic add per warp).  Mirrors the reference's scan
+ * primitive `alp_func` + `aggr_plus`
+ * (publication/source_code/bench_end_to_end/src/benchmarks/alp/queries/q1.cpp:63-102). */
+int alpb200_decode_sum_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum,
+                           void* stream);
+int alpb200_decode_sum_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum,
+                           void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host engine calls; copies are part of the call).
  * A codec context owns device staging buffers, pinned bounce buffers and streams so that repeated

@@ -250,3 +250,36 @@ def test_large_column_properties():
     owner = np.repeat(np.arange(meta.shape[0]), cnt)
     key = owner * 1024 + pos
     assert np.all(np.diff(key) > 0)  # ascending positions inside every vector, vectors in order
+
+
+@pytest.mark.parametrize("kind", [2, 3, 4])
+def test_fused_decode_sum(kind):
+    """alpb200_decode_sum: decode + aggregate without materialising (reference: alp_func + aggr_plus, q1.cpp:63-102).
+    Floating point: the order of additions differs from a sequential sum, so the check is relative (1e-9) against a
+    float64 sum of the bit-exact decoded column."""
+    import torch
+
+    import alp_b200
+
+    n = 5 * 102400 + 13 * 1024
+    xd = alp_b200.generate(n, kind, _dev())
+    col = alp_b200.encode(xd)
+    col.read_totals()
+    want = float(alp_b200.decode(col).double().sum().item())
+    got = float(alp_b200.decode_sum(col).item())
+    assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (kind, got, want)
+    part = float(alp_b200.decode_sum(col, first=100, n=237).item())
+    want_part = float(xd[100 * 1024 : 337 * 1024].double().sum().item())
+    assert abs(part - want_part) <= 1e-9 * max(1.0, abs(want_part))
+
+
+def test_fused_decode_sum_propagates_nan():
+    import torch
+
+    import alp_b200
+
+    x = torch.arange(4096, dtype=torch.float64, device=_dev()) / 8.0
+    x[1234] = float("nan")
+    col = alp_b200.encode(x)
+    col.read_totals()
+    assert torch.isnan(alp_b200.decode_sum(col)).item()
