@@ -82,10 +82,11 @@ class Column(ctypes.Structure):
         ("exc_capacity", ctypes.c_uint64),
         ("totals", ctypes.c_void_p),
         ("max_block_bytes", ctypes.c_uint64),
+        ("n_values", ctypes.c_uint64),
     ]
 
 
-assert ctypes.sizeof(Column) == 72
+assert ctypes.sizeof(Column) == 80
 
 
 def value_types(value_bytes):
@@ -118,6 +119,7 @@ class HostColumn:
         self.exc_val = np.zeros(int(exc_capacity), dtype=value_types(value_bytes)[1])
         self.exc_pos = np.zeros(int(exc_capacity), dtype=np.uint16)
         self.totals = np.zeros(4, dtype=np.uint64)
+        self.n_values = 0  # 0 = n_vectors * 1024 (set by HostCodec.compress when the last vector is padded)
 
     def as_struct(self):
         return Column(
@@ -130,6 +132,7 @@ class HostColumn:
             self.exc_val.shape[0],
             self.totals.ctypes.data,
             int(self.totals[3]),
+            int(self.n_values),
         )
 
     @property

@@ -70,6 +70,7 @@ class DeviceColumn:
             self.exc_capacity,
             self.totals.data_ptr(),
             self.max_block_bytes,
+            0,
         )
 
     def read_totals(self):
@@ -220,17 +221,19 @@ class HostCodec:
 
     def compress(self, values, col=None):
         values = np.ascontiguousarray(values)
-        n_vec = values.shape[0] // _abi.VECTOR_SIZE
+        n_vec = -(-values.shape[0] // _abi.VECTOR_SIZE)  # a partial last vector is padded by the library
         if col is None:
             col = _abi.HostColumn(n_vec, self.value_bytes)
         st = col.as_struct()
         fn = getattr(lib, "alpb200_compress_host_" + _sfx(self.value_bytes))
         check(fn(self._ctx, values.ctypes.data, values.shape[0], ctypes.byref(st)))
+        col.n_vectors = int(st.n_vectors)
+        col.n_values = int(st.n_values)
         return col
 
     def decompress(self, col, out=None):
         if out is None:
-            out = np.empty(col.n_vectors * _abi.VECTOR_SIZE, dtype=_abi.value_types(self.value_bytes)[0])
+            out = np.empty(col.n_values or col.n_vectors * _abi.VECTOR_SIZE, dtype=_abi.value_types(self.value_bytes)[0])
         st = col.as_struct()
         fn = getattr(lib, "alpb200_decompress_host_" + _sfx(self.value_bytes))
         check(fn(self._ctx, ctypes.byref(st), out.ctypes.data))

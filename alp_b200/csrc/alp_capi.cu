@@ -19,7 +19,7 @@
 
 static_assert(sizeof(alpb200_rg_state) == 1196, "alpb200_rg_state layout");
 static_assert(sizeof(alpb200_vec_meta) == 32, "alpb200_vec_meta layout");
-static_assert(sizeof(alpb200_column) == 72, "alpb200_column layout");
+static_assert(sizeof(alpb200_column) == 80, "alpb200_column layout");
 
 using namespace alpb200;
 
@@ -452,18 +452,38 @@ void ctx_release(alpb200_ctx* c) {
 	delete c;
 }
 
+// tail vector: the values after n_values up to the next multiple of 1024 repeat the last value, which
+// keeps the vector's (e,f) choice and bit width what the real values ask for
 template <typename PT>
-int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values, alpb200_column* h_col) {
+__global__ void pad_tail_kernel(PT* __restrict__ v, uint64_t n_values, uint64_t n_padded) {
+	const PT last = v[n_values - 1];
+	for (uint64_t i = n_values + threadIdx.x; i < n_padded; i += blockDim.x) {
+		v[i] = last;
+	}
+}
+
+template <typename PT>
+int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_column* h_col) {
 	if (!c || !h_in || !h_col || !h_col->meta || !h_col->packed || !h_col->exc_val || !h_col->exc_pos || !h_col->totals) {
 		return fail(ALPB200_EINVAL, "compress_host: null argument");
 	}
 	if (c->value_bytes != (int)sizeof(PT)) { return fail(ALPB200_EINVAL, "compress_host: context was created for another value width"); }
-	if (n_values % VEC != 0) { return fail(ALPB200_EINVAL, "compress_host: n_values must be a multiple of 1024"); }
-	const uint64_t n_vec = n_values / VEC;
+	const uint64_t n_vec    = (n_values_in + VEC - 1) / VEC;
+	const uint64_t n_values = n_vec * VEC;  // padded length
 	if (n_vec > c->max_vectors || n_vec > h_col->n_vectors) { return fail(ALPB200_EINVAL, "compress_host: column larger than the context / container"); }
 	CUDA_TRY(cudaSetDevice(c->device));
 	cudaStream_t s = c->streams[0];
-	CUDA_TRY(cudaMemcpyAsync(c->d_values, h_in, n_values * sizeof(PT), cudaMemcpyHostToDevice, s));
+	if (n_vec == 0) {
+		h_col->n_vectors = 0;
+		h_col->n_values  = 0;
+		std::memset(h_col->totals, 0, 4 * sizeof(uint64_t));
+		return ALPB200_OK;
+	}
+	CUDA_TRY(cudaMemcpyAsync(c->d_values, h_in, n_values_in * sizeof(PT), cudaMemcpyHostToDevice, s));
+	if (n_values != n_values_in) {
+		pad_tail_kernel<PT><<<1, 256, 0, s>>>(static_cast<PT*>(c->d_values), n_values_in, n_values);
+		CUDA_TRY(cudaGetLastError());
+	}
 	TRY(launch_init<PT>(static_cast<const PT*>(c->d_values), n_values, c->d_states, c->d_ws_init, s));
 	alpb200_column d_col {};
 	d_col.n_vectors       = n_vec;
@@ -489,6 +509,7 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values, alpb200_col
 	CUDA_TRY(cudaStreamSynchronize(s));
 	CUDA_TRY(cudaStreamSynchronize(c->streams[1]));
 	h_col->n_vectors       = n_vec;
+	h_col->n_values        = n_values_in;
 	h_col->max_block_bytes = c->h_totals[3];
 	std::memcpy(h_col->totals, c->h_totals, 4 * sizeof(uint64_t));
 	return ALPB200_OK;
@@ -504,6 +525,8 @@ int decompress_host(alpb200_ctx* c, const alpb200_column* h_col, PT* h_out) {
 	const uint64_t n_vec = h_col->n_vectors;
 	if (n_vec > c->max_vectors) { return fail(ALPB200_EINVAL, "decompress_host: column larger than the context"); }
 	if (n_vec == 0) { return ALPB200_OK; }
+	const uint64_t n_out = h_col->n_values ? h_col->n_values : n_vec * VEC;  // a padded tail is not returned
+	if (n_out > n_vec * VEC || n_out + VEC <= n_vec * VEC) { return fail(ALPB200_EINVAL, "decompress_host: n_values does not match n_vectors"); }
 	CUDA_TRY(cudaSetDevice(c->device));
 	const alpb200_vec_meta* hm = h_col->meta;
 	auto block_units = [](const alpb200_vec_meta& m) -> uint64_t { return m.scheme == ALPB200_SCHEME_ALP_RD ? (uint64_t)m.bw + m.e : m.bw; };
@@ -537,7 +560,8 @@ int decompress_host(alpb200_ctx* c, const alpb200_column* h_col, PT* h_out) {
 		}
 		PT* d_out = static_cast<PT*>(c->d_values) + v0 * VEC;
 		TRY(launch_decode<PT>(&d_col, v0, v1 - v0, d_out, s));
-		CUDA_TRY(cudaMemcpyAsync(h_out + v0 * VEC, d_out, (v1 - v0) * VEC * sizeof(PT), cudaMemcpyDeviceToHost, s));
+		const uint64_t n_copy = std::min<uint64_t>((v1 - v0) * VEC, n_out - v0 * VEC);
+		CUDA_TRY(cudaMemcpyAsync(h_out + v0 * VEC, d_out, n_copy * sizeof(PT), cudaMemcpyDeviceToHost, s));
 	}
 	for (int i = 0; i < 3; i++) {
 		CUDA_TRY(cudaStreamSynchronize(c->streams[i]));

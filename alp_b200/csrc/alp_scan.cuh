@@ -33,27 +33,27 @@ __device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const Met
 	const int64_t  fact = T::fact10(m.f());
 	const double   frac = T::frac10(m.e());
 	const uint64_t base = m.base();
-	double         acc  = 0.0;
+	double         acc[4] = {0.0, 0.0, 0.0, 0.0};  // independent chains: the adds of consecutive rows do not wait for each other
 	dispatch_width<0, 64>(m.bw(), [&](auto W) {
 		constexpr int BW = decltype(W)::value;
-		unpack64_rows<BW>(stage, t & 15, t >> 4, [&](int, uint32_t lo, uint32_t hi) {
+		unpack64_rows<BW>(stage, t & 15, t >> 4, [&](int r, uint32_t lo, uint32_t hi) {
 			const uint64_t d = BW <= 32 ? (uint64_t)lo : ((uint64_t)hi << 32) | lo;
-			acc += decode_value<double>((int64_t)(d + base), fact, frac);
+			acc[r & 3] += decode_value<double>((int64_t)(d + base), fact, frac);
 		});
 	});
-	return acc;
+	return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 __device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, float) {
 	using T             = Traits<float>;
 	const int32_t  fact = T::fact10(m.f());
 	const float    frac = T::frac10(m.e());
 	const uint32_t base = m.a.x;
-	double         acc  = 0.0;
+	double         acc[4] = {0.0, 0.0, 0.0, 0.0};
 	dispatch_width<0, 32>(m.bw(), [&](auto W) {
 		constexpr int BW = decltype(W)::value;
-		unpack32_rows<BW>(stage, t, [&](int, uint32_t d) { acc += (double)decode_value<float>((int32_t)(d + base), fact, frac); });
+		unpack32_rows<BW>(stage, t, [&](int r, uint32_t d) { acc[r & 3] += (double)decode_value<float>((int32_t)(d + base), fact, frac); });
 	});
-	return acc;
+	return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 // ALP_RD value at position p: (left << right_bw) | right, left from the dictionary or, for exceptions, given
@@ -76,7 +76,7 @@ __device__ __forceinline__ double rd_value(const uint8_t* stage, const MetaRegs&
 }
 
 template <typename PT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) decode_sum_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
+__global__ void __launch_bounds__(WARPS * 32, 3) decode_sum_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
                                                                   double* __restrict__ sum, uint32_t stage_bytes,
                                                                   unsigned long long* __restrict__ counter) {
 	using UT = typename Traits<PT>::UT;

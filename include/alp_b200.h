@@ -112,6 +112,10 @@ typedef struct alpb200_column {
 	/* decode hint: the largest packed block of any vector in bytes (totals[3] after encode), or 0 when unknown —
 	 * the decoder then sizes its shared-memory stages for the widest possible block */
 	uint64_t          max_block_bytes;
+	/* number of values the column holds; when it is not a multiple of 1024 the last vector was padded by the encoder
+	 * (alpb200_compress_host_*) and only n_values are returned by alpb200_decompress_host_*.  0 = n_vectors * 1024.
+	 * (The reference's drivers drop the tail, benchmarks/benchmark.cpp:191; PRIMITIVES.md:141-144 suggests padding.) */
+	uint64_t          n_values;
 } alpb200_column;
 
 int         alpb200_version(void);
@@ -178,9 +182,10 @@ typedef struct alpb200_ctx alpb200_ctx;
 int  alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes);
 void alpb200_ctx_destroy(alpb200_ctx* ctx);
 
-/* Compress a host column of n_values (multiple of 1024) values into a host column container whose arrays the
- * caller allocated (capacities in h_col).  H2D of the values, init, encode, D2H of the compressed arrays.
- * h_totals[0..1] receive packed bytes / exception slots used. */
+/* Compress a host column of n_values values (any length: a partial last vector is padded on the device with the
+ * column's last value and n_values is recorded in the container) into a host column container whose arrays the
+ * caller allocated (capacities in h_col; n_vectors >= ceil(n_values / 1024)).  H2D of the values, init, encode,
+ * D2H of the compressed arrays.  h_col->totals[0..1] receive packed bytes / exception slots used. */
 int alpb200_compress_host_f64(alpb200_ctx* ctx, const double* h_in, uint64_t n_values, alpb200_column* h_col);
 int alpb200_compress_host_f32(alpb200_ctx* ctx, const float* h_in, uint64_t n_values, alpb200_column* h_col);
 /* Decompress a host column container into h_out: H2D of the compressed arrays, decode, D2H of the values,

@@ -283,3 +283,22 @@ def test_fused_decode_sum_propagates_nan():
     col = alp_b200.encode(x)
     col.read_totals()
     assert torch.isnan(alp_b200.decode_sum(col)).item()
+
+
+@pytest.mark.parametrize("n_tail", [1, 777, 1023])
+def test_host_codec_pads_a_partial_last_vector(n_tail, checker):
+    """Columns whose length is not a multiple of 1024: the tail vector is padded on the device, the
+    true length travels in the container, and decompress returns exactly the original values."""
+    import alp_b200
+    from oracle import pyoracle
+
+    n = 102400 + 5 * 1024 + n_tail
+    x = pyoracle.generate(n + 1024, 2)[:n].copy()
+    codec = alp_b200.HostCodec(n // 1024 + 1, 8)
+    col = codec.compress(x)
+    assert col.n_vectors == n // 1024 + 1 and col.n_values == n
+    assert codec.decompress(col).tobytes() == x.tobytes()
+    # the padded column is an ordinary column for everybody else: the checker decodes it, padding = the last value
+    full = checker.decode_column(col)
+    assert full[:n].tobytes() == x.tobytes() and np.all(full[n:] == x[-1])
+    codec.close()
