@@ -94,7 +94,8 @@ def scatter_column(col, src=0, group=None, value_bytes=8, device=None):
                 continue
             for key in ("meta", "packed", "exc_val", "exc_pos"):
                 if s[key].numel():
-                    reqs.append(dist.isend(s[key].contiguous(), dst=r, group=group))
+                    # as bytes: NCCL has no 16-bit integer type (exc_pos)
+                    reqs.append(dist.isend(s[key].contiguous().view(torch.uint8).reshape(-1), dst=r, group=group))
         for q in reqs:
             q.wait()
         mine = shards[src]
@@ -108,7 +109,7 @@ def scatter_column(col, src=0, group=None, value_bytes=8, device=None):
         }
         for key in ("meta", "packed", "exc_val", "exc_pos"):
             if mine[key].numel():
-                dist.recv(mine[key], src=src, group=group)
+                dist.recv(mine[key].view(torch.uint8).reshape(-1), src=src, group=group)
     return mine, plan[rank]
 
 
