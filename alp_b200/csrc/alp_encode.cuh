@@ -163,6 +163,7 @@ struct GlobalIO {
 	}
 	template <int R>
 	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT) {}
+	static constexpr bool KEEPS = false;  // encoded integers are not kept anywhere
 };
 template <typename PT>
 struct TileIO {
@@ -178,6 +179,8 @@ struct TileIO {
 	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT v) {
 		tile[Map<PT>::index(t, R)] = v;
 	}
+	static constexpr bool KEEPS = true;  // the tile holds the encoded integers afterwards
+	__device__ __forceinline__ UT kept(int position) const { return tile[position]; }
 };
 
 // ---- ALP analysis: encoder.hpp:307-400 + :109-120 ------------------------------------------------------------------
@@ -215,8 +218,10 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 		const uint32_t em  = exc ? 0xFFFFFFFFu : 0u;  // branch-free: exceptions are neutral for min / max / and / or
 		io.store(R, (UT)enc);
 		myexc |= em & (1u << r);
-		first = (unseen & ~em) ? enc : first;
-		unseen &= em;
+		if constexpr (!IO::KEEPS) {
+			first = (unseen & ~em) ? enc : first;
+			unseen &= em;
+		}
 		if constexpr (sizeof(PT) == 8) {
 			const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
 			lo_min = min(lo_min, lo | em);
@@ -237,8 +242,12 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 	a.fill = 0;
 	if (cand != 0xFFFFu) {
 		const int owner = Map<PT>::thread_of((int)cand);
+		if constexpr (IO::KEEPS) {
+			__syncwarp();
+			a.fill = (ST)io.kept((int)cand);
+		}
 		if constexpr (sizeof(PT) == 8) {
-			a.fill = (ST)shfl_u64((uint64_t)first, owner);
+			if constexpr (!IO::KEEPS) { a.fill = (ST)shfl_u64((uint64_t)first, owner); }
 			hi_and = __reduce_and_sync(FULL, hi_and);
 			hi_or  = __reduce_or_sync(FULL, hi_or);
 			if (hi_and == hi_or) {  // one common high word: order is decided by the low words
@@ -257,7 +266,7 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 				mx = warp_max<ST>(mx);
 			}
 		} else {
-			a.fill = (ST)__shfl_sync(FULL, (int)first, owner);
+			if constexpr (!IO::KEEPS) { a.fill = (ST)__shfl_sync(FULL, (int)first, owner); }
 			mn     = warp_min<ST>(mn);
 			mx     = warp_max<ST>(mx);
 		}
@@ -435,37 +444,41 @@ template <typename PT, typename ValueOf, typename Store>
 __device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&& value_of, Store&& store) {
 	if (!__any_sync(FULL, myexc != 0)) { return; }
 	const uint32_t rowmask = transpose32(myexc, t);  // lane r: ballot of "is exception" over row r
-	uint32_t       rows    = __ballot_sync(FULL, rowmask != 0);
+	// Lane r now knows how many exceptions precede row r; every thread then walks ITS OWN exceptions and fetches the
+	// prefix of each one's row from lane r.  The loop runs max-exceptions-per-thread times (2-4 for a typical vector)
+	// instead of once per row that holds an exception.
+	uint32_t m = myexc;
 	if (sizeof(PT) == 8) {
 		const int lane = t & 15, half = t >> 4;
 		uint32_t  tot_lo, tot_hi;
 		const uint32_t p_lo = warp_excl_scan(__popc(rowmask & 0xFFFFu), t, tot_lo);
 		const uint32_t p_hi = warp_excl_scan(__popc(rowmask >> 16), t, tot_hi) + tot_lo;
-		while (rows) {
-			const int r = __ffs(rows) - 1;
-			rows &= rows - 1;
-			const uint32_t m  = __shfl_sync(FULL, rowmask, r);
-			const uint32_t pl = __shfl_sync(FULL, p_lo, r), ph = __shfl_sync(FULL, p_hi, r);
-			if ((m >> t) & 1u) {
-				const uint32_t hm   = half ? (m >> 16) : (m & 0xFFFFu);
-				const uint32_t rank = (half ? ph : pl) + __popc(hm & ((1u << lane) - 1));
+		const uint32_t pre  = p_lo | (p_hi << 16);  // both at most 1024
+		while (__any_sync(FULL, m != 0)) {
+			const int      r  = m ? __ffs((int)m) - 1 : 0;
+			const uint32_t rm = __shfl_sync(FULL, rowmask, r);
+			const uint32_t pr = __shfl_sync(FULL, pre, r);
+			if (m) {
+				const uint32_t hm   = half ? (rm >> 16) : (rm & 0xFFFFu);
+				const uint32_t rank = (half ? (pr >> 16) : (pr & 0xFFFFu)) + __popc(hm & ((1u << lane) - 1));
 				const uint32_t p    = 16u * (32 * half + r) + lane;
 				store(rank, p, value_of(p));
 			}
+			m &= m - 1;
 		}
 	} else {
 		uint32_t       tot;
 		const uint32_t pre = warp_excl_scan(__popc(rowmask), t, tot);
-		while (rows) {
-			const int r = __ffs(rows) - 1;
-			rows &= rows - 1;
-			const uint32_t m  = __shfl_sync(FULL, rowmask, r);
+		while (__any_sync(FULL, m != 0)) {
+			const int      r  = m ? __ffs((int)m) - 1 : 0;
+			const uint32_t rm = __shfl_sync(FULL, rowmask, r);
 			const uint32_t pr = __shfl_sync(FULL, pre, r);
-			if ((m >> t) & 1u) {
-				const uint32_t rank = pr + __popc(m & ((1u << t) - 1));
+			if (m) {
+				const uint32_t rank = pr + __popc(rm & ((1u << t) - 1));
 				const uint32_t p    = 32u * r + t;
 				store(rank, p, value_of(p));
 			}
+			m &= m - 1;
 		}
 	}
 }

@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every kernel, small sizes."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import alp_b200  # noqa: E402
+
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(0)
+cols = [
+    alp_b200.generate(3 * 102400, 2, dev),
+    alp_b200.generate(2 * 102400 + 7 * 1024, 3, dev),
+    alp_b200.generate(2 * 102400, 4, dev),
+    torch.from_numpy(np.full(2048, np.nan)).to(dev),
+    torch.from_numpy(rng.integers(0, 1 << 63, size=1024 * 9, dtype=np.uint64).view(np.float64)).to(dev),
+    torch.from_numpy(rng.integers(0, 1 << 32, size=1024 * 9, dtype=np.uint64).astype(np.uint32).view(np.float32)).to(dev),
+    torch.zeros(4096, dtype=torch.float32, device=dev),
+]
+for x in cols:
+    col = alp_b200.encode(x)
+    col.read_totals()
+    y = alp_b200.decode(col)
+    ib = torch.int64 if x.element_size() == 8 else torch.int32
+    assert torch.equal(x.view(ib), y.view(ib))
+    s = alp_b200.decode_sum(col)
+    torch.cuda.synchronize()
+from alp_b200 import primitives as gpu  # noqa: E402
+
+v = (rng.integers(0, 100000, 1024) / 100.0)
+st = gpu.init(v)
+r = gpu.encode(v, st)
+bw, base = gpu.analyze_ffor(r["enc"])
+p = gpu.ffor(r["enc"].view(np.uint64), bw, int(base))
+d = gpu.patch(gpu.falp(p, bw, int(base), r["f"], r["e"]), r["exc"], r["pos"])
+assert d.tobytes() == v.tobytes()
+codec = alp_b200.HostCodec(300, 8)
+h = codec.compress(np.ascontiguousarray(cols[0].cpu().numpy()[:200000]))
+assert codec.decompress(h).tobytes() == cols[0].cpu().numpy()[:200000].tobytes()
+codec.close()
+print("sanitize smoke OK")
