@@ -23,11 +23,11 @@ constexpr uint32_t MAX_BLOCK     = 8192 + 3 * 128;  // largest packed block: ALP
 // F32 FACT[10] is the reference's out-of-bounds read (decoder.hpp:129 with MAX_EXPONENT 10, constants.hpp:39,63);
 // 0 is what the g++ build of the reference returns there (see oracle/alp_oracle.c).
 // ---------------------------------------------------------------------------------------------------------------
-__constant__ double  C_F64_EXP[24]  = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+static __constant__ double  C_F64_EXP[24]  = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
                                        1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22, 1e23};
-__constant__ double  C_F64_FRAC[21] = {1.0,   0.1,   0.01,  0.001, 1e-4,  1e-5,  1e-6,  1e-7,  1e-8,  1e-9, 1e-10,
+static __constant__ double  C_F64_FRAC[21] = {1.0,   0.1,   0.01,  0.001, 1e-4,  1e-5,  1e-6,  1e-7,  1e-8,  1e-9, 1e-10,
                                        1e-11, 1e-12, 1e-13, 1e-14, 1e-15, 1e-16, 1e-17, 1e-18, 1e-19, 1e-20};
-__constant__ int64_t C_F64_FACT[19] = {1LL,
+static __constant__ int64_t C_F64_FACT[19] = {1LL,
                                        10LL,
                                        100LL,
                                        1000LL,
@@ -46,10 +46,10 @@ __constant__ int64_t C_F64_FACT[19] = {1LL,
                                        10000000000000000LL,
                                        100000000000000000LL,
                                        1000000000000000000LL};
-__constant__ float   C_F32_EXP[11]  = {1e0f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
-__constant__ float   C_F32_FRAC[11] = {1.0f,      0.1f,       0.01f,       0.001f,       0.0001f,      0.00001f,
+static __constant__ float   C_F32_EXP[11]  = {1e0f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+static __constant__ float   C_F32_FRAC[11] = {1.0f,      0.1f,       0.01f,       0.001f,       0.0001f,      0.00001f,
                                        0.000001f, 0.0000001f, 0.00000001f, 0.000000001f, 0.0000000001f};
-__constant__ int32_t C_F32_FACT[11] = {1, 10, 100, 1000, 10000, 100000, 1000000, 10000000, 100000000, 1000000000, 0};
+static __constant__ int32_t C_F32_FACT[11] = {1, 10, 100, 1000, 10000, 100000, 1000000, 10000000, 100000000, 1000000000, 0};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Per-type traits.  All floating-point steps use the explicitly rounded intrinsics so that nvcc can never contract

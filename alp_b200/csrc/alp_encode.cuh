@@ -381,7 +381,7 @@ __device__ __forceinline__ void pack_rows(const uint32_t* __restrict__ tile, uin
 // Re-reads the vector (L2-resident: this warp streamed it a moment ago), re-encodes it with the chosen (e,f) — no
 // decode/compare, the exception bitmap is known — and packs.  dst may be shared or global memory.
 // (not inlined: keeps the 33 width instances out of the kernel body)
-__device__ __noinline__ void pack_from_input(const float* __restrict__ in_vec, uint32_t bw, uint32_t e, uint32_t f, uint32_t base,
+static __device__ __noinline__ void pack_from_input(const float* __restrict__ in_vec, uint32_t bw, uint32_t e, uint32_t f, uint32_t base,
                                              uint32_t fill, uint32_t myexc, bool rd, int t, uint8_t* __restrict__ dst) {
 	using T = Traits<float>;
 	const float ex = T::exp10(rd ? 0 : e), frf = T::frac10(rd ? 0 : f);

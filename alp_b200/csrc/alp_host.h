@@ -1,0 +1,56 @@
+// alp_host.h — what the translation units of libalp_b200.so share on the host side: error reporting, the per-device
+// bookkeeping and the kernel launchers.  The library is split into one TU per kernel family (decode, encode f64,
+// encode f32, init + primitives) so that nvcc compiles them in parallel; nothing here is part of the public ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "alp_b200.h"
+
+namespace alpb200 {
+
+// records the message returned by alpb200_last_error() (thread-local) and returns `code`
+int fail(int code, const char* fmt, const char* a = "", const char* b = "");
+
+#define CUDA_TRY(expr)                                                                                    \
+	do {                                                                                                  \
+		cudaError_t err__ = (expr);                                                                       \
+		if (err__ != cudaSuccess) { return ::alpb200::fail(ALPB200_ECUDA, "%s: %s", #expr, cudaGetErrorString(err__)); } \
+	} while (0)
+
+#define TRY(expr)                               \
+	do {                                        \
+		if (int rc__ = (expr)) { return rc__; } \
+	} while (0)
+
+constexpr int DEC_WARPS = 8;
+constexpr int ENC_WARPS = 8;
+
+struct DeviceInfo {
+	int sms        = 0;
+	int smem_optin = 0;
+	// work-distribution counters of the decode kernels: one slot per launch, handed out round-robin, zeroed on the
+	// launch's stream right before the kernel (allocated once per device; nothing on the hot path)
+	unsigned long long* counters     = nullptr;
+	uint32_t            next_counter = 0;
+};
+int device_info(DeviceInfo& out);
+
+// ---- launchers (explicitly instantiated for double and float in their TU) ----
+template <typename PT>
+int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_out, void* stream);
+template <typename PT>
+int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream);
+template <typename PT>
+int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream);
+template <typename PT>
+int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream);
+template <typename PT>
+int launch_pad_tail(PT* d_values, uint64_t n_values, uint64_t n_padded, void* stream);
+
+size_t encode_workspace_bytes(uint64_t n_vectors);
+size_t init_workspace_bytes(uint64_t n_values);
+
+}  // namespace alpb200

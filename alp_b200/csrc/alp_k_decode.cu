@@ -1,0 +1,73 @@
+// alp_k_decode.cu — launchers of the decode and fused decode+SUM kernels (one translation unit of libalp_b200.so).
+#include <algorithm>
+
+#include "alp_decode.cuh"
+#include "alp_host.h"
+#include "alp_scan.cuh"
+
+namespace alpb200 {
+
+template <typename PT>
+int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_out, void* stream) {
+	if (!col) { return fail(ALPB200_EINVAL, "decode: null argument"); }
+	if (first + n > col->n_vectors) { return fail(ALPB200_EINVAL, "decode: vector range outside the column"); }
+	if (n == 0) { return ALPB200_OK; }
+	if (!d_out || !col->meta || !col->packed) { return fail(ALPB200_EINVAL, "decode: null argument"); }
+	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0) { return fail(ALPB200_EINVAL, "decode: column.packed must be 128-byte aligned"); }
+	DeviceInfo di;
+	if (int rc = device_info(di)) { return rc; }
+	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
+	uint32_t       block  = col->max_block_bytes ? (uint32_t)std::min<uint64_t>(col->max_block_bytes, widest) : widest;
+	const uint32_t stage  = ((block + 127u) & ~127u) + STAGE_PAD;
+	// narrow blocks: decode into a shared-memory tile and bulk-store it; wide blocks (ALP_RD, bw > 32): direct line stores
+	const bool   tile = stage <= 4096 + STAGE_PAD;
+	const size_t smem = (size_t)DEC_WARPS * ((tile ? VEC * sizeof(PT) : 0) + 2 * stage) + DEC_WARPS * 2 * sizeof(uint64_t);
+	auto         kern = tile ? decode_kernel<PT, DEC_WARPS, true> : decode_kernel<PT, DEC_WARPS, false>;
+	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_WARPS * 32, smem));
+	if (per_sm < 1) { return fail(ALPB200_ECUDA, "decode: kernel does not fit on an SM"); }
+	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
+	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	unsigned long long* counter = di.counters + di.next_counter;
+	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
+	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_out, stage, counter);
+	CUDA_TRY(cudaGetLastError());
+	return ALPB200_OK;
+}
+
+template <typename PT>
+int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream) {
+	if (!col || !d_sum) { return fail(ALPB200_EINVAL, "decode_sum: null argument"); }
+	if (first + n > col->n_vectors) { return fail(ALPB200_EINVAL, "decode_sum: vector range outside the column"); }
+	if (n == 0) { return ALPB200_OK; }
+	if (!col->meta || !col->packed) { return fail(ALPB200_EINVAL, "decode_sum: null argument"); }
+	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0) { return fail(ALPB200_EINVAL, "decode_sum: column.packed must be 128-byte aligned"); }
+	DeviceInfo di;
+	if (int rc = device_info(di)) { return rc; }
+	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
+	uint32_t       block  = col->max_block_bytes ? (uint32_t)std::min<uint64_t>(col->max_block_bytes, widest) : widest;
+	const uint32_t stage  = ((block + 127u) & ~127u) + STAGE_PAD;
+	const size_t   smem   = (size_t)DEC_WARPS * 2 * stage + DEC_WARPS * 2 * sizeof(uint64_t);
+	auto           kern   = decode_sum_kernel<PT, DEC_WARPS>;
+	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_WARPS * 32, smem));
+	if (per_sm < 1) { return fail(ALPB200_ECUDA, "decode_sum: kernel does not fit on an SM"); }
+	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
+	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	unsigned long long* counter = di.counters + di.next_counter;
+	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
+	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_sum, stage, counter);
+	CUDA_TRY(cudaGetLastError());
+	return ALPB200_OK;
+}
+
+template int launch_decode<double>(const alpb200_column*, uint64_t, uint64_t, double*, void*);
+template int launch_decode<float>(const alpb200_column*, uint64_t, uint64_t, float*, void*);
+template int launch_decode_sum<double>(const alpb200_column*, uint64_t, uint64_t, double*, void*);
+template int launch_decode_sum<float>(const alpb200_column*, uint64_t, uint64_t, double*, void*);
+
+}  // namespace alpb200
