@@ -39,16 +39,21 @@ SIGNATURES = {
     "alpb200_encode_workspace_bytes": ([_c.c_uint64], _c.c_size_t),
     "alpb200_encode_f64": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
     "alpb200_encode_f32": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
+    "alpb200_encode_unordered_f64": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
+    "alpb200_encode_unordered_f32": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
     "alpb200_decode_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_sum_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_sum_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_ctx_create": ([_P, _c.c_int, _c.c_uint64, _c.c_int], _c.c_int),
     "alpb200_ctx_destroy": ([_P], None),
+    "alpb200_ctx_set_option": ([_P, _c.c_int, _c.c_int], _c.c_int),
     "alpb200_compress_host_f64": ([_P, _P, _c.c_uint64, _P], _c.c_int),
     "alpb200_compress_host_f32": ([_P, _P, _c.c_uint64, _P], _c.c_int),
     "alpb200_decompress_host_f64": ([_P, _P, _P], _c.c_int),
     "alpb200_decompress_host_f32": ([_P, _P, _P], _c.c_int),
+    "alpb200_sum_host_f64": ([_P, _P, _P], _c.c_int),
+    "alpb200_sum_host_f32": ([_P, _P, _P], _c.c_int),
     "alpb200_host_alloc": ([_c.c_size_t], _P),
     "alpb200_host_free": ([_P], None),
     "alpb200_prim_encode_f64": ([_P] * 8, _c.c_int),

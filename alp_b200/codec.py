@@ -139,8 +139,9 @@ def rowgroup_init(values):
     return states
 
 
-def encode(values, states=None, col=None, workspace=None):
-    """Compress a device column (numel a multiple of 1024) → DeviceColumn.  `states` defaults to rowgroup_init(values)."""
+def encode(values, states=None, col=None, workspace=None, ordered=True):
+    """Compress a device column (numel a multiple of 1024) → DeviceColumn.  `states` defaults to rowgroup_init(values).
+    ordered=False selects the completion-order layout (alpb200_encode_unordered_*): same blocks, faster, bytes not reproducible."""
     _require_cuda(values, "values")
     vb = values.element_size()
     if values.dtype != _FLOAT[vb] or values.numel() % _abi.VECTOR_SIZE:
@@ -155,7 +156,7 @@ def encode(values, states=None, col=None, workspace=None):
         workspace = torch.empty(max(256, lib.alpb200_encode_workspace_bytes(n_vec)), dtype=torch.uint8, device=values.device)
     st = col.as_struct()
     with torch.cuda.device(values.device):
-        fn = getattr(lib, "alpb200_encode_" + _sfx(vb))
+        fn = getattr(lib, ("alpb200_encode_" if ordered else "alpb200_encode_unordered_") + _sfx(vb))
         check(fn(values.data_ptr(), n_vec, states.data_ptr(), ctypes.byref(st), workspace.data_ptr(), _stream_ptr(values.device)))
     return col
 
@@ -202,11 +203,15 @@ def generate(n_values, kind, device, seed=None, first_index=0, out=None):
 class HostCodec:
     """alpb200_ctx: compress / decompress columns that live in HOST memory (copies are part of each call)."""
 
-    def __init__(self, max_vectors, value_bytes=8, device=0):
+    OPT_UNORDERED = 1  # ALPB200_OPT_UNORDERED
+
+    def __init__(self, max_vectors, value_bytes=8, device=0, ordered=True):
         self.value_bytes = value_bytes
         self.max_vectors = int(max_vectors)
         self._ctx = ctypes.c_void_p()
         check(lib.alpb200_ctx_create(ctypes.byref(self._ctx), device, self.max_vectors, value_bytes))
+        if not ordered:
+            check(lib.alpb200_ctx_set_option(self._ctx, self.OPT_UNORDERED, 1))
 
     def close(self):
         if self._ctx:
@@ -230,6 +235,14 @@ class HostCodec:
         col.n_vectors = int(st.n_vectors)
         col.n_values = int(st.n_values)
         return col
+
+    def sum(self, col):
+        """SUM of a host column: only the compressed bytes go to the device, one double comes back (alpb200_sum_host_*)."""
+        st = col.as_struct()
+        out = ctypes.c_double(0.0)
+        fn = getattr(lib, "alpb200_sum_host_" + _sfx(self.value_bytes))
+        check(fn(self._ctx, ctypes.byref(st), ctypes.byref(out)))
+        return float(out.value)
 
     def decompress(self, col, out=None):
         if out is None:

@@ -82,6 +82,7 @@ struct alpb200_ctx {
 	void*             d_ws_init = nullptr;
 	uint64_t          packed_capacity = 0, exc_capacity = 0;
 	uint64_t*         h_totals = nullptr;  // pinned
+	bool              unordered = false;   // ALPB200_OPT_UNORDERED: compress_host encodes with the completion-order layout
 };
 
 namespace {
@@ -137,7 +138,7 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_
 	d_col.exc_pos         = c->d_exc_pos;
 	d_col.exc_capacity    = c->exc_capacity;
 	d_col.totals          = c->d_totals;
-	TRY(launch_encode<PT>(static_cast<const PT*>(c->d_values), n_vec, c->d_states, &d_col, c->d_ws_enc, s));
+	TRY(launch_encode<PT>(static_cast<const PT*>(c->d_values), n_vec, c->d_states, &d_col, c->d_ws_enc, s, !c->unordered));
 	CUDA_TRY(cudaMemcpyAsync(c->h_totals, c->d_totals, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(cudaMemcpyAsync(h_col->meta, c->d_meta, n_vec * sizeof(alpb200_vec_meta), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(cudaStreamSynchronize(s));
@@ -158,6 +159,27 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_
 	return ALPB200_OK;
 }
 
+// Byte / slot ranges of the compressed arrays that the vectors [v0, v1) touch.  For a vector-order column that is
+// [offset of v0, offset of v1); a completion-order column (alpb200_encode_unordered_*) is only roughly sorted, so the
+// range is the min / max over the records (neighbouring chunks then overlap by a few blocks, which are simply copied
+// twice).
+struct ChunkRange {
+	uint64_t p0, p1, e0, e1;
+};
+inline uint64_t block_units(const alpb200_vec_meta& m) { return m.scheme == ALPB200_SCHEME_ALP_RD ? (uint64_t)m.bw + m.e : m.bw; }
+ChunkRange chunk_range(const alpb200_vec_meta* hm, uint64_t v0, uint64_t v1) {
+	ChunkRange r {UINT64_MAX, 0, UINT64_MAX, 0};
+	for (uint64_t v = v0; v < v1; v++) {
+		const alpb200_vec_meta& m = hm[v];
+		const uint64_t          p = (uint64_t)m.packed_off * 128ull, e = m.exc_off;
+		r.p0 = std::min(r.p0, p);
+		r.p1 = std::max<uint64_t>(r.p1, p + block_units(m) * 128ull);
+		r.e0 = std::min(r.e0, e);
+		r.e1 = std::max<uint64_t>(r.e1, e + m.exc_cnt);
+	}
+	if (v0 >= v1) { r = ChunkRange {0, 0, 0, 0}; }
+	return r;
+}
 // Chunked pipeline: while chunk i decodes and drains to the host on one stream, chunk i+1's compressed bytes are
 // already travelling on another (PCIe is full duplex).  Chunks are whole ranges of vectors; thanks to the vector-order
 // layout each chunk's packed bytes and exceptions are one contiguous range.
@@ -172,12 +194,6 @@ int decompress_host(alpb200_ctx* c, const alpb200_column* h_col, PT* h_out) {
 	if (n_out > n_vec * VEC || n_out + VEC <= n_vec * VEC) { return fail(ALPB200_EINVAL, "decompress_host: n_values does not match n_vectors"); }
 	CUDA_TRY(cudaSetDevice(c->device));
 	const alpb200_vec_meta* hm = h_col->meta;
-	auto block_units = [](const alpb200_vec_meta& m) -> uint64_t { return m.scheme == ALPB200_SCHEME_ALP_RD ? (uint64_t)m.bw + m.e : m.bw; };
-	const alpb200_vec_meta& last = hm[n_vec - 1];
-	const uint64_t total_packed  = ((uint64_t)last.packed_off + block_units(last)) * 128ull;
-	const uint64_t total_exc     = (uint64_t)last.exc_off + last.exc_cnt;
-	if (total_packed > c->packed_capacity || total_exc > c->exc_capacity) { return fail(ALPB200_ECAPACITY, "decompress_host: column exceeds the context's staging capacity"); }
-
 	alpb200_column d_col {};
 	d_col.n_vectors       = n_vec;
 	d_col.meta            = c->d_meta;
@@ -189,11 +205,16 @@ int decompress_host(alpb200_ctx* c, const alpb200_column* h_col, PT* h_out) {
 	const uint64_t chunk = std::max<uint64_t>(1024, (n_vec + 15) / 16);  // ~16 chunks, at least 8 MiB of f64 output each
 	int            si    = 0;
 	for (uint64_t v0 = 0; v0 < n_vec; v0 += chunk, si = (si + 1) % 3) {
-		const uint64_t v1 = std::min(n_vec, v0 + chunk);
-		cudaStream_t   s  = c->streams[si];
-		const uint64_t p0 = (uint64_t)hm[v0].packed_off * 128ull, e0 = hm[v0].exc_off;
-		const uint64_t p1 = v1 < n_vec ? (uint64_t)hm[v1].packed_off * 128ull : total_packed;
-		const uint64_t e1 = v1 < n_vec ? hm[v1].exc_off : total_exc;
+		const uint64_t   v1 = std::min(n_vec, v0 + chunk);
+		cudaStream_t     s  = c->streams[si];
+		const ChunkRange cr = chunk_range(hm, v0, v1);  // scanned chunk by chunk: the first copy starts at once
+		if (cr.p1 > c->packed_capacity || cr.e1 > c->exc_capacity) {
+			for (int i = 0; i < 3; i++) {
+				cudaStreamSynchronize(c->streams[i]);
+			}
+			return fail(ALPB200_ECAPACITY, "decompress_host: column exceeds the context's staging capacity");
+		}
+		const uint64_t p0 = cr.p0, p1 = cr.p1, e0 = cr.e0, e1 = cr.e1;
 		CUDA_TRY(cudaMemcpyAsync(c->d_meta + v0, hm + v0, (v1 - v0) * sizeof(alpb200_vec_meta), cudaMemcpyHostToDevice, s));
 		if (p1 > p0) { CUDA_TRY(cudaMemcpyAsync(c->d_packed + p0, h_col->packed + p0, p1 - p0, cudaMemcpyHostToDevice, s)); }
 		if (e1 > e0) {
@@ -209,6 +230,80 @@ int decompress_host(alpb200_ctx* c, const alpb200_column* h_col, PT* h_out) {
 	for (int i = 0; i < 3; i++) {
 		CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
 	}
+	return ALPB200_OK;
+}
+
+// SUM of a host column: the chunk pipeline of decompress_host with the fused decode+SUM kernel and no values coming
+// back.  Every chunk adds into the same device double (atomics), read back once at the end.
+template <typename PT>
+int sum_host(alpb200_ctx* c, const alpb200_column* h_col, double* h_sum) {
+	if (!c || !h_col || !h_sum || !h_col->meta) { return fail(ALPB200_EINVAL, "sum_host: null argument"); }
+	if (c->value_bytes != (int)sizeof(PT)) { return fail(ALPB200_EINVAL, "sum_host: context was created for another value width"); }
+	const uint64_t n_vec = h_col->n_vectors;
+	if (n_vec > c->max_vectors) { return fail(ALPB200_EINVAL, "sum_host: column larger than the context"); }
+	*h_sum = 0.0;
+	if (n_vec == 0) { return ALPB200_OK; }
+	const uint64_t n_out = h_col->n_values ? h_col->n_values : n_vec * VEC;
+	if (n_out > n_vec * VEC || n_out + VEC <= n_vec * VEC) { return fail(ALPB200_EINVAL, "sum_host: n_values does not match n_vectors"); }
+	CUDA_TRY(cudaSetDevice(c->device));
+	const alpb200_vec_meta* hm = h_col->meta;
+	alpb200_column d_col {};
+	d_col.n_vectors       = n_vec;
+	d_col.meta            = c->d_meta;
+	d_col.packed          = c->d_packed;
+	d_col.exc_val         = c->d_exc_val;
+	d_col.exc_pos         = c->d_exc_pos;
+	d_col.max_block_bytes = h_col->max_block_bytes;
+	double* d_sum         = reinterpret_cast<double*>(c->d_totals);  // 32 bytes of device scratch owned by the context
+	CUDA_TRY(cudaMemsetAsync(d_sum, 0, sizeof(double), c->streams[0]));
+	CUDA_TRY(cudaEventRecord(c->events[0], c->streams[0]));
+	for (int i = 1; i < 3; i++) {
+		CUDA_TRY(cudaStreamWaitEvent(c->streams[i], c->events[0], 0));
+	}
+	// a padded tail vector is summed on its own so that the padding can be taken out again (it repeats the last value)
+	const bool     ragged = n_out != n_vec * VEC;
+	const uint64_t n_full = ragged ? n_vec - 1 : n_vec;
+	const uint64_t chunk = std::max<uint64_t>(1024, (n_vec + 15) / 16);  // ~16 chunks, at least 8 MiB of f64 output each
+	int            si    = 0;
+	for (uint64_t v0 = 0; v0 < n_vec; v0 += chunk, si = (si + 1) % 3) {
+		const uint64_t   v1 = std::min(n_vec, v0 + chunk);
+		cudaStream_t     s  = c->streams[si];
+		const ChunkRange cr = chunk_range(hm, v0, v1);  // scanned chunk by chunk: the first copy starts at once
+		if (cr.p1 > c->packed_capacity || cr.e1 > c->exc_capacity) {
+			for (int i = 0; i < 3; i++) {
+				cudaStreamSynchronize(c->streams[i]);
+			}
+			return fail(ALPB200_ECAPACITY, "sum_host: column exceeds the context's staging capacity");
+		}
+		const uint64_t p0 = cr.p0, p1 = cr.p1, e0 = cr.e0, e1 = cr.e1;
+		CUDA_TRY(cudaMemcpyAsync(c->d_meta + v0, hm + v0, (v1 - v0) * sizeof(alpb200_vec_meta), cudaMemcpyHostToDevice, s));
+		if (p1 > p0) { CUDA_TRY(cudaMemcpyAsync(c->d_packed + p0, h_col->packed + p0, p1 - p0, cudaMemcpyHostToDevice, s)); }
+		if (e1 > e0) {
+			CUDA_TRY(cudaMemcpyAsync(static_cast<PT*>(c->d_exc_val) + e0, static_cast<const PT*>(h_col->exc_val) + e0, (e1 - e0) * sizeof(PT),
+			                         cudaMemcpyHostToDevice, s));
+			CUDA_TRY(cudaMemcpyAsync(c->d_exc_pos + e0, h_col->exc_pos + e0, (e1 - e0) * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+		}
+		const uint64_t stop = std::min(v1, n_full);
+		if (stop > v0) { TRY(launch_decode_sum<PT>(&d_col, v0, stop - v0, d_sum, s)); }
+	}
+	for (int i = 0; i < 3; i++) {
+		CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
+	}
+	double total = 0.0;
+	if (ragged) {  // decode the last vector (4-8 KiB) and add its real values on the host
+		cudaStream_t s = c->streams[0];
+		PT*          d_tail = static_cast<PT*>(c->d_values);
+		TRY(launch_decode<PT>(&d_col, n_vec - 1, 1, d_tail, s));
+		std::vector<PT> tail(VEC);
+		CUDA_TRY(cudaMemcpyAsync(tail.data(), d_tail, VEC * sizeof(PT), cudaMemcpyDeviceToHost, s));
+		CUDA_TRY(cudaStreamSynchronize(s));
+		for (uint64_t i = 0; i < n_out - n_full * VEC; i++) {
+			total += (double)tail[i];
+		}
+	}
+	double dev_sum = 0.0;
+	CUDA_TRY(cudaMemcpy(&dev_sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost));
+	*h_sum = dev_sum + total;
 	return ALPB200_OK;
 }
 
@@ -254,6 +349,15 @@ int alpb200_encode_f64(const double* d_in, uint64_t n_vectors, const alpb200_rg_
 int alpb200_encode_f32(const float* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws,
                        void* stream) {
 	return launch_encode<float>(d_in, n_vectors, d_states, col, ws, stream);
+}
+
+int alpb200_encode_unordered_f64(const double* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws,
+                                 void* stream) {
+	return launch_encode<double>(d_in, n_vectors, d_states, col, ws, stream, false);
+}
+int alpb200_encode_unordered_f32(const float* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws,
+                                 void* stream) {
+	return launch_encode<float>(d_in, n_vectors, d_states, col, ws, stream, false);
 }
 
 int alpb200_decode_f64(const alpb200_column* col, uint64_t first, uint64_t n, double* d_out, void* stream) {
@@ -315,6 +419,13 @@ int alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int 
 	return ALPB200_OK;
 }
 void alpb200_ctx_destroy(alpb200_ctx* ctx) { ctx_release(ctx); }
+int  alpb200_ctx_set_option(alpb200_ctx* ctx, int option, int value) {
+	if (!ctx) { return fail(ALPB200_EINVAL, "ctx_set_option: null context"); }
+	switch (option) {
+	case ALPB200_OPT_UNORDERED: ctx->unordered = value != 0; return ALPB200_OK;
+	default: return fail(ALPB200_EINVAL, "ctx_set_option: unknown option");
+	}
+}
 
 int alpb200_compress_host_f64(alpb200_ctx* ctx, const double* h_in, uint64_t n_values, alpb200_column* h_col) {
 	return compress_host<double>(ctx, h_in, n_values, h_col);
@@ -324,6 +435,8 @@ int alpb200_compress_host_f32(alpb200_ctx* ctx, const float* h_in, uint64_t n_va
 }
 int alpb200_decompress_host_f64(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_out) { return decompress_host<double>(ctx, h_col, h_out); }
 int alpb200_decompress_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, float* h_out) { return decompress_host<float>(ctx, h_col, h_out); }
+int alpb200_sum_host_f64(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_sum) { return sum_host<double>(ctx, h_col, h_sum); }
+int alpb200_sum_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_sum) { return sum_host<float>(ctx, h_col, h_sum); }
 
 void* alpb200_host_alloc(size_t bytes) {
 	void* p = nullptr;

@@ -166,73 +166,65 @@ __device__ __forceinline__ void patch_alp(const ColView& col, const MetaRegs& m,
 }
 
 // ---- ALP_RD (rd.hpp:152-178): right parts on T-bit lanes, dictionary indices on 16-bit lanes -----------------------
-__device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const ColView& col, const MetaRegs& m,
-                                                 const ExcRegs<uint64_t>& x, double* __restrict__ out_vec, int t) {
+// rd_unpack_rows: emit(r, bits) receives the glued bit pattern (dict[idx] << right_bw) | right of the thread's row r
+// (value index Map<PT>::index(t, r)); exceptions are NOT applied.  Shared by the decode and the decode+SUM kernels.
+template <typename Emit>
+__device__ __forceinline__ void rd_unpack_rows(const uint8_t* stage, const MetaRegs& m, int t, double /*tag*/, Emit&& emit) {
 	const uint32_t  rbw = m.bw(), lbw = m.e();
 	const int       lane = t & 15, half = t >> 4;
-	const uint64_t* rblk  = reinterpret_cast<const uint64_t*>(stage);
 	const uint16_t* lblk  = reinterpret_cast<const uint16_t*>(stage + 128u * rbw);
-	const uint64_t  rmask = low_mask<uint64_t>(rbw);
 	const uint32_t  lmask = (1u << lbw) - 1;
-	uint64_t*       o     = reinterpret_cast<uint64_t*>(out_vec) + 512 * half + lane;
 	dispatch_width<48, 63>(rbw < 48 ? 48u : rbw, [&](auto W) {  // right_bit_width = 64 - cut, cut in 1..16 (rd.hpp:95)
 		constexpr int BW = decltype(W)::value;
 		unpack64_rows<BW>(stage, lane, half, [&](int r, uint32_t lo, uint32_t hi) {
 			const uint64_t right = ((uint64_t)hi << 32) | lo;
 			const uint32_t v     = 16u * (32u * half + r) + lane;  // 16-bit-lane coordinates of the same value
 			const uint32_t idx   = extract16(lblk, v & 63, (v >> 6) * lbw, lmask);
-			store_out(&o[16 * r], ((uint64_t)dict_lookup(m.a, idx) << BW) | right);
+			emit(r, ((uint64_t)dict_lookup(m.a, idx) << BW) | right);
 		});
 	});
-	__syncwarp();
-	// exceptions: the true left part replaces the dictionary entry (rd.hpp:172-177)
-	const uint32_t cnt = m.exc_cnt();
-	uint64_t*      ov  = reinterpret_cast<uint64_t*>(out_vec);
-	if ((uint32_t)t < cnt) {
-		const uint64_t right = extract64(rblk, x.pos & 15, (x.pos >> 4) * rbw, rmask);
-		ov[x.pos]            = ((x.val & 0xFFFFu) << rbw) | right;
-	}
-	if (cnt > 32) {
-		const uint64_t* ev = static_cast<const uint64_t*>(col.exc_val) + m.exc_off();
-		const uint16_t* ep = col.exc_pos + m.exc_off();
-		for (uint32_t i = t + 32; i < cnt; i += 32) {
-			const uint32_t p     = ep[i];
-			const uint64_t right = extract64(rblk, p & 15, (p >> 4) * rbw, rmask);
-			ov[p]                = ((ev[i] & 0xFFFFu) << rbw) | right;
-		}
-	}
 }
-
-__device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const ColView& col, const MetaRegs& m,
-                                                 const ExcRegs<uint32_t>& x, float* __restrict__ out_vec, int t) {
+template <typename Emit>
+__device__ __forceinline__ void rd_unpack_rows(const uint8_t* stage, const MetaRegs& m, int t, float /*tag*/, Emit&& emit) {
 	const uint32_t  rbw = m.bw(), lbw = m.e();
-	const uint32_t* rblk  = reinterpret_cast<const uint32_t*>(stage);
 	const uint16_t* lblk  = reinterpret_cast<const uint16_t*>(stage + 128u * rbw);
-	const uint32_t  rmask = low_mask<uint32_t>(rbw);
 	const uint32_t  lmask = (1u << lbw) - 1;
-	uint32_t*       o     = reinterpret_cast<uint32_t*>(out_vec) + t;
 	dispatch_width<16, 31>(rbw < 16 ? 16u : rbw, [&](auto W) {
 		constexpr int BW = decltype(W)::value;
 		unpack32_rows<BW>(stage, t, [&](int r, uint32_t right) {
 			const uint32_t v   = 32u * r + t;
 			const uint32_t idx = extract16(lblk, v & 63, (v >> 6) * lbw, lmask);
-			store_out(&o[32 * r], (dict_lookup(m.a, idx) << BW) | right);
+			emit(r, (dict_lookup(m.a, idx) << BW) | right);
 		});
 	});
+}
+// right part of position p, re-extracted from the stage (exception patch)
+__device__ __forceinline__ uint64_t rd_right_at(const uint8_t* stage, uint32_t rbw, uint32_t p, uint64_t /*tag*/) {
+	return extract64(reinterpret_cast<const uint64_t*>(stage), p & 15, (p >> 4) * rbw, low_mask<uint64_t>(rbw));
+}
+__device__ __forceinline__ uint32_t rd_right_at(const uint8_t* stage, uint32_t rbw, uint32_t p, uint32_t /*tag*/) {
+	return extract32(reinterpret_cast<const uint32_t*>(stage), p & 31, (p >> 5) * rbw, low_mask<uint32_t>(rbw));
+}
+
+template <typename PT>
+__device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const ColView& col, const MetaRegs& m,
+                                                 const ExcRegs<typename Traits<PT>::UT>& x, PT* __restrict__ out_vec, int t) {
+	using UT           = typename Traits<PT>::UT;
+	const uint32_t rbw = m.bw();
+	UT*            ov  = reinterpret_cast<UT*>(out_vec);
+	UT*            o   = ov + Map<PT>::index(t, 0);
+	constexpr int  ROW = Traits<PT>::LANES;  // distance between consecutive rows of a thread
+	rd_unpack_rows(stage, m, t, PT(), [&](int r, UT bits) { store_out(&o[ROW * r], bits); });
 	__syncwarp();
+	// exceptions: the true left part replaces the dictionary entry (rd.hpp:172-177)
 	const uint32_t cnt = m.exc_cnt();
-	uint32_t*      ov  = reinterpret_cast<uint32_t*>(out_vec);
-	if ((uint32_t)t < cnt) {
-		const uint32_t right = extract32(rblk, x.pos & 31, (x.pos >> 5) * rbw, rmask);
-		ov[x.pos]            = ((x.val & 0xFFFFu) << rbw) | right;
-	}
+	if ((uint32_t)t < cnt) { ov[x.pos] = ((x.val & 0xFFFFu) << rbw) | rd_right_at(stage, rbw, x.pos, UT()); }
 	if (cnt > 32) {
-		const uint32_t* ev = static_cast<const uint32_t*>(col.exc_val) + m.exc_off();
+		const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
 		const uint16_t* ep = col.exc_pos + m.exc_off();
 		for (uint32_t i = t + 32; i < cnt; i += 32) {
-			const uint32_t p     = ep[i];
-			const uint32_t right = extract32(rblk, p & 31, (p >> 5) * rbw, rmask);
-			ov[p]                = ((ev[i] & 0xFFFFu) << rbw) | right;
+			const uint32_t p = ep[i];
+			ov[p]            = ((ev[i] & 0xFFFFu) << rbw) | rd_right_at(stage, rbw, p, UT());
 		}
 	}
 }
@@ -333,7 +325,7 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 			__syncwarp();  // orders the patch stores after the lane-interleaved main stores
 			patch_alp<PT>(col, cur, xcur, out_vec, t);
 		} else {
-			decode_rd_vector(stg, col, cur, xcur, out_vec, t);
+			decode_rd_vector<PT>(stg, col, cur, xcur, out_vec, t);
 		}
 		if constexpr (OUT_TILE) {
 			fence_proxy_async_smem();  // generic-proxy writes to the tile -> visible to the bulk-copy engine

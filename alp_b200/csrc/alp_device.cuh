@@ -165,6 +165,26 @@ __device__ __forceinline__ int bits_of_range(typename Traits<PT>::ST mx, typenam
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Thread -> value mapping.  64-bit lanes: thread (lane = t&15, half = t>>4) owns rows 32*half .. 32*half+31 of FastLanes
+// lane `lane`, i.e. values 16*(32*half + r) + lane.  32-bit lanes: thread t owns lane t, values 32*r + t.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename PT>
+struct Map;
+template <>
+struct Map<double> {
+	__device__ static __forceinline__ int index(int t, int r) { return 512 * (t >> 4) + 16 * r + (t & 15); }
+	// thread and row that own value index v
+	__device__ static __forceinline__ int thread_of(int v) { return (v & 15) + 16 * (v >> 9); }
+	__device__ static __forceinline__ int row_of(int v) { return (v >> 4) & 31; }
+};
+template <>
+struct Map<float> {
+	__device__ static __forceinline__ int index(int t, int r) { return 32 * r + t; }
+	__device__ static __forceinline__ int thread_of(int v) { return v & 31; }
+	__device__ static __forceinline__ int row_of(int v) { return v >> 5; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // Warp helpers
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t shfl_xor_i64(int64_t v, int m) {

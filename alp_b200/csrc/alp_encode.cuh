@@ -25,23 +25,6 @@
 
 namespace alpb200 {
 
-// thread -> value mapping of the two lane widths
-template <typename PT>
-struct Map;
-template <>
-struct Map<double> {
-	__device__ static __forceinline__ int index(int t, int r) { return 512 * (t >> 4) + 16 * r + (t & 15); }
-	// thread and row that own value index v
-	__device__ static __forceinline__ int thread_of(int v) { return (v & 15) + 16 * (v >> 9); }
-	__device__ static __forceinline__ int row_of(int v) { return (v >> 4) & 31; }
-};
-template <>
-struct Map<float> {
-	__device__ static __forceinline__ int index(int t, int r) { return 32 * r + t; }
-	__device__ static __forceinline__ int thread_of(int v) { return v & 31; }
-	__device__ static __forceinline__ int row_of(int v) { return v >> 5; }
-};
-
 // the head of alpb200_rg_state (44 bytes), loaded once per warp
 struct StateRegs {
 	uint32_t scheme, k, c0, c1, c2, ds;
@@ -163,6 +146,13 @@ struct GlobalIO {
 	}
 	template <int R>
 	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT) {}
+	// start over (the analysis is redone with the exact per-value recipe)
+	__device__ __forceinline__ void rewind(const PT* in_vec) {
+#pragma unroll
+		for (int i = 0; i < B; i++) {
+			nxt[i] = Traits<PT>::bits(in_vec[Map<PT>::index(t, i)]);
+		}
+	}
 	static constexpr bool KEEPS = false;  // encoded integers are not kept anywhere
 };
 template <typename PT>
@@ -179,6 +169,13 @@ struct TileIO {
 	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT v) {
 		tile[Map<PT>::index(t, R)] = v;
 	}
+	// start over: the tile was overwritten with encoded integers; every thread restores ITS OWN slots from global memory
+	__device__ __forceinline__ void rewind(const PT* in_vec) {
+#pragma unroll 8
+		for (int r = 0; r < 32; r++) {
+			tile[Map<PT>::index(t, r)] = Traits<PT>::bits(in_vec[Map<PT>::index(t, r)]);
+		}
+	}
 	static constexpr bool KEEPS = true;  // the tile holds the encoded integers afterwards
 	__device__ __forceinline__ UT kept(int position) const { return tile[position]; }
 };
@@ -193,7 +190,109 @@ struct TileIO {
 // min/max of the non-exceptions (analyze_ffor, encoder.hpp:109-120; exception slots hold `fill`, itself a
 // non-exception).  64-bit integers have no native min/max (2 ISETP + 2 SEL each), so the common case — all high
 // words equal, e.g. every encoded integer in [0, 2^32) — tracks unsigned min/max of the low words plus AND/OR of the
-// high words, branch-free, and falls back to a second pass over the input otherwise.
+// high words, and falls back to a second pass over the input otherwise.
+//
+// Two implementations of the per-value step, bit-identical in outcome:
+//
+//  EXACT  the reference's recipe literally: enc = x86-cast(t_r), dec = (PT)(enc * FACT[f]) * FRAC[e]  (t_r = the
+//         magic-rounded scaled value).  For doubles that is a range test + two selects around F2I, a 64-bit integer
+//         multiply (5 instructions) and an I2F.F64.S64.
+//  FAST   stays in floating point: Pd = t_r * 10^f, dec = Pd * FRAC[e].  Why it is the same number: t_r is
+//         integer-valued, so while |t_r| < 2^63 the cast is exact (enc == t_r) and the integer product P = enc * 10^f is
+//         the real product of two exactly representable numbers (10^f <= 10^18 is exact in double, 10^9 in float); as
+//         long as |P| < 2^63 it does not wrap, the reference's integer-to-float conversion returns RN(P), and so does
+//         the floating-point multiply: Pd == (PT)(enc * FACT[f]).
+//         When the product does NOT fit (|P| >= 2^63 | 2^31, or t_r itself is out of range / NaN and the cast returns
+//         ST_MIN) the reference's value is always an exception: x * 10^e lies within 10^f / 2 <= |P| / 2 of P, i.e. it
+//         has P's sign and at least half its magnitude, whereas the wrapped product has the opposite sign for
+//         2^63 <= |P| < 2^64 and at most half the magnitude beyond — the decoded value cannot equal x.  So FAST forces
+//         an exception whenever |Pd| > 2^63 (2^31), judged on the bit pattern of Pd (`key`: |Pd| as an unsigned
+//         integer, high word for doubles; NaN and Inf compare above).  Only |Pd| == 2^63 leaves the question open
+//         (P within rounding distance of the boundary; -2^63 itself is representable): the warp then abandons FAST and
+//         redoes the vector with EXACT.  For doubles the test looks at the high word only, which widens that case to
+//         2^63 <= |Pd| < 2^63 * (1 + 2^-20) — still a one-in-a-million sliver.
+//         (float, f = 10: FACT[10] is the reference's out-of-bounds 0, so P = 0 and nothing wraps; 10^f is taken as 0.)
+template <typename PT>
+struct FastLimits;
+template <>
+struct FastLimits<double> {
+	static constexpr uint32_t BIG = 0x43E00000u;  // high word of 2^63
+	__device__ static __forceinline__ uint32_t key(double pd) { return (uint32_t)((uint64_t)__double_as_longlong(pd) >> 32) & 0x7FFFFFFFu; }
+	__device__ static __forceinline__ double fact_fp(int f) { return C_F64_EXP[f]; }  // 10^f, exact
+	__device__ static __forceinline__ int64_t cast_sat(double tr) { return __double2ll_rz(tr); }
+};
+template <>
+struct FastLimits<float> {
+	static constexpr uint32_t BIG = 0x4F000000u;  // 2^31
+	__device__ static __forceinline__ uint32_t key(float pd) { return __float_as_uint(pd) & 0x7FFFFFFFu; }
+	__device__ static __forceinline__ float fact_fp(int f) { return f < 10 ? C_F32_EXP[f] : 0.0f; }  // FACT[10] = 0 (alp_device.cuh)
+	__device__ static __forceinline__ int32_t cast_sat(float tr) { return __float2int_rz(tr); }
+};
+
+// what the 32 rows of a thread accumulate
+template <typename PT>
+struct RowAcc {
+	using ST = typename Traits<PT>::ST;
+	uint32_t myexc  = 0;
+	uint32_t lo_min = 0xFFFFFFFFu, lo_max = 0, hi_and = 0xFFFFFFFFu, hi_or = 0;  // f64
+	ST       mn = Traits<PT>::ST_MAX, mx = Traits<PT>::ST_MIN;                   // f32
+	ST       first  = 0;            // encoded integer of this thread's first non-exception
+	uint32_t unseen = 0xFFFFFFFFu;  // all-ones until the thread has met a non-exception
+};
+
+// One pass over the thread's 32 rows.  Returns false (FAST only) when some lane met a value on the boundary described above.
+template <typename PT, bool FAST, typename IO>
+__device__ __forceinline__ bool analyze_rows(IO& io, int e, int f, RowAcc<PT>& acc) {
+	using T  = Traits<PT>;
+	using UT = typename T::UT;
+	using ST = typename T::ST;
+	using FL = FastLimits<PT>;
+	const PT       ex = T::exp10(e), frf = T::frac10(f), fre = T::frac10(e);
+	const ST       fa  = T::fact10(f);
+	const PT       fap = FL::fact_fp(f);
+	bool           suspicious = false;
+	static_for<0, 32>([&](auto R) {
+		constexpr int r  = decltype(R)::value;
+		const UT      xb = io.load(R);
+		ST            enc;
+		bool          exc;
+		if constexpr (FAST) {
+			const PT       tr  = T::magic_round(T::mul(T::mul(T::from_bits(xb), ex), frf));  // encoder.hpp:83,87
+			const PT       pd  = T::mul(tr, fap);
+			const uint32_t key = FL::key(pd);
+			enc                = FL::cast_sat(tr);
+			suspicious |= key == FL::BIG;
+			const PT dec = T::mul(pd, fre);
+			exc          = (T::bits(dec) != xb) | (key > FL::BIG);
+		} else {
+			enc          = encode_value<PT, false>(T::from_bits(xb), ex, frf);  // encoder.hpp:345
+			const PT dec = decode_value<PT>(enc, fa, fre);                       // :347
+			exc          = T::bits(dec) != xb;
+		}
+		io.store(R, (UT)enc);
+		if (exc) { acc.myexc |= 1u << r; }
+		if constexpr (!IO::KEEPS) {
+			const uint32_t em = exc ? 0xFFFFFFFFu : 0u;
+			acc.first         = (acc.unseen & ~em) ? enc : acc.first;
+			acc.unseen &= em;
+		}
+		if (!exc) {  // exceptions take no part in min / max (predicated, no branch)
+			if constexpr (sizeof(PT) == 8) {
+				const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
+				acc.lo_min = min(acc.lo_min, lo);
+				acc.lo_max = max(acc.lo_max, lo);
+				acc.hi_and &= hi;
+				acc.hi_or |= hi;
+			} else {
+				acc.mn = min(acc.mn, enc);
+				acc.mx = max(acc.mx, enc);
+			}
+		}
+	});
+	if constexpr (FAST) { return !__any_sync(FULL, suspicious); }
+	return true;
+}
+
 template <typename PT, typename IO>
 __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const StateRegs& st, int t, IO& io, Analysis<PT>& a) {
 	using T  = Traits<PT>;
@@ -201,38 +300,15 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 	using ST = typename T::ST;
 	int e = st.exp_of(0), f = st.fac_of(0);
 	if (st.k > 1) { choose_exponent_factor<PT>(in_vec[32 * t], st, e, f); }  // encoder.hpp:409-412
-	const PT ex = T::exp10(e), frf = T::frac10(f), fre = T::frac10(e);
-	const ST fa = T::fact10(f);
 
-	uint32_t myexc = 0;
-	uint32_t lo_min = 0xFFFFFFFFu, lo_max = 0, hi_and = 0xFFFFFFFFu, hi_or = 0;  // f64
-	ST       mn = T::ST_MAX, mx = T::ST_MIN;                                       // f32
-	ST       first = 0;       // encoded integer of this thread's first non-exception
-	uint32_t unseen = 0xFFFFFFFFu;  // all-ones until the thread has met a non-exception
-	static_for<0, 32>([&](auto R) {
-		constexpr int  r   = decltype(R)::value;
-		const UT       xb  = io.load(R);
-		const ST       enc = encode_value<PT, false>(T::from_bits(xb), ex, frf);  // encoder.hpp:345
-		const PT       dec = decode_value<PT>(enc, fa, fre);                       // :347
-		const bool     exc = T::bits(dec) != xb;
-		const uint32_t em  = exc ? 0xFFFFFFFFu : 0u;  // branch-free: exceptions are neutral for min / max / and / or
-		io.store(R, (UT)enc);
-		myexc |= em & (1u << r);
-		if constexpr (!IO::KEEPS) {
-			first = (unseen & ~em) ? enc : first;
-			unseen &= em;
-		}
-		if constexpr (sizeof(PT) == 8) {
-			const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
-			lo_min = min(lo_min, lo | em);
-			lo_max = max(lo_max, lo & ~em);
-			hi_and &= hi | em;
-			hi_or |= hi & ~em;
-		} else {
-			mn = min(mn, exc ? T::ST_MAX : enc);
-			mx = max(mx, exc ? T::ST_MIN : enc);
-		}
-	});
+	RowAcc<PT> acc;
+	if (!analyze_rows<PT, true>(io, e, f, acc)) {
+		acc = RowAcc<PT>();
+		io.rewind(in_vec);
+		analyze_rows<PT, false>(io, e, f, acc);
+	}
+	const uint32_t myexc = acc.myexc;
+	ST             mn = acc.mn, mx = acc.mx;
 	a.myexc = myexc;
 	a.cnt   = __reduce_add_sync(FULL, (uint32_t)__popc(myexc));
 	// fill value = encoded integer at the first non-exception position, 0 if there is none (encoder.hpp:382-388)
@@ -247,13 +323,14 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 			a.fill = (ST)io.kept((int)cand);
 		}
 		if constexpr (sizeof(PT) == 8) {
-			if constexpr (!IO::KEEPS) { a.fill = (ST)shfl_u64((uint64_t)first, owner); }
-			hi_and = __reduce_and_sync(FULL, hi_and);
-			hi_or  = __reduce_or_sync(FULL, hi_or);
+			if constexpr (!IO::KEEPS) { a.fill = (ST)shfl_u64((uint64_t)acc.first, owner); }
+			const uint32_t hi_and = __reduce_and_sync(FULL, acc.hi_and);
+			const uint32_t hi_or  = __reduce_or_sync(FULL, acc.hi_or);
 			if (hi_and == hi_or) {  // one common high word: order is decided by the low words
-				mn = (ST)(((uint64_t)hi_or << 32) | __reduce_min_sync(FULL, lo_min));
-				mx = (ST)(((uint64_t)hi_or << 32) | __reduce_max_sync(FULL, lo_max));
+				mn = (ST)(((uint64_t)hi_or << 32) | __reduce_min_sync(FULL, acc.lo_min));
+				mx = (ST)(((uint64_t)hi_or << 32) | __reduce_max_sync(FULL, acc.lo_max));
 			} else {  // wide range: full 64-bit pass, re-encoding from the input
+				const PT ex = T::exp10(e), frf = T::frac10(f);
 #pragma unroll 4
 				for (int r = 0; r < 32; r++) {
 					const ST v = encode_value<PT, false>(in_vec[Map<PT>::index(t, r)], ex, frf);
@@ -266,7 +343,7 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 				mx = warp_max<ST>(mx);
 			}
 		} else {
-			if constexpr (!IO::KEEPS) { a.fill = (ST)__shfl_sync(FULL, (int)first, owner); }
+			if constexpr (!IO::KEEPS) { a.fill = (ST)__shfl_sync(FULL, (int)acc.first, owner); }
 			mn     = warp_min<ST>(mn);
 			mx     = warp_max<ST>(mx);
 		}
@@ -362,8 +439,8 @@ __device__ __forceinline__ void pack_rows(const uint64_t* __restrict__ tile, uin
 	});
 }
 // 32-bit lanes: word j of lane t at element 32*j + t — every store instruction writes one full 128-byte line
-__device__ __forceinline__ void pack_rows(const uint32_t* __restrict__ tile, uint32_t myexc, uint32_t fill, uint32_t base,
-                                          uint32_t bw, int t, uint8_t* __restrict__ dst) {
+__device__ __forceinline__ void pack_rows(const uint32_t* tile, uint32_t myexc, uint32_t fill, uint32_t base, uint32_t bw, int t,
+                                          uint8_t* dst) {
 	dispatch_width<0, 32>(bw, [&](auto W) {
 		constexpr int BW = decltype(W)::value;
 		if constexpr (BW > 0) {
@@ -375,6 +452,31 @@ __device__ __forceinline__ void pack_rows(const uint32_t* __restrict__ tile, uin
 			});
 		}
 	});
+}
+
+// FFOR IN PLACE: the tile of encoded integers becomes the packed block image (bytes [0, 128*bw) of the tile), ready to
+// leave with one bulk-async store.  Runs BEFORE the block's output offset is known, i.e. it overlaps the placement wait.
+// 64-bit lanes, bw <= 32 only (wider blocks keep more words live than the register budget allows; they take the
+// direct path).  Only the low words are read: (v - base) mod 2^32 is all a field of <= 32 bits needs.
+__device__ __forceinline__ void pack_rows_inplace(uint64_t* tile, uint32_t myexc, uint64_t fill, uint64_t base, uint32_t bw, int t) {
+	const int       lane = t & 15, half = t >> 4;
+	const uint32_t* lo32 = reinterpret_cast<const uint32_t*>(tile);
+	dispatch_width<0, 32>(bw, [&](auto W) {
+		constexpr int BW = decltype(W)::value;
+		if constexpr (BW > 0) {
+			pack64_rows<BW, true>(lane, half, tile, [&](auto R, uint32_t& lo, uint32_t& hi) {
+				constexpr int r = decltype(R)::value;
+				uint32_t      v = lo32[2 * Map<double>::index(t, r)];
+				if ((myexc >> r) & 1u) { v = (uint32_t)fill; }
+				lo = v - (uint32_t)base;
+				hi = 0;
+			});
+		}
+	});
+}
+// 32-bit lanes: pack32_rows is in-place safe as it is (alp_ffor.cuh)
+__device__ __forceinline__ void pack_rows_inplace(uint32_t* tile, uint32_t myexc, uint32_t fill, uint32_t base, uint32_t bw, int t) {
+	pack_rows(tile, myexc, fill, base, bw, t, reinterpret_cast<uint8_t*>(tile));
 }
 
 // ---- second pass of the batched encoder: FFOR straight from the input ------------------------------------------------
@@ -577,32 +679,47 @@ struct ColOut {
 // workspace layout: [0] ticket counter, [1] reserved, [2 .. 2+n_blocks) block aggregates, [2+n_blocks .. 2+2*n_blocks)
 // exclusive prefixes.
 //
-// One CTA = WARPS vectors, one warp each.  Two strategies, chosen per value type from measurements on B200:
+// One CTA = WARPS vectors, one warp each.  Per warp:
+//   1  the vector arrives in a per-warp shared-memory tile with one bulk-async copy (TMA 1-D)
+//   2  analysis in place: the tile now holds the encoded integers (ALP) / right parts (ALP_RD)
+//   3  the CTA publishes its aggregate (packed units, exceptions) and the scanner starts working out its offsets
+//   4  WHILE the offsets are on their way: FFOR in place — the head of the tile becomes the packed block image
+//   5  once the offsets are known the block leaves with one bulk-async store (TMA 1-D); exceptions and the record follow
+// Wide 64-bit-lane blocks (bw > 32: ALP_RD on doubles, huge integers) cannot be packed in place within the register
+// budget; they are FFOR-ed from the tile straight into the column after step 3's wait (full 128-byte line stores).
 //
-//  * ONE PASS (f64): the vector arrives in a per-warp shared-memory tile with one bulk-async copy (TMA 1-D), is encoded
-//    in place, and is packed from the tile once the CTA's output offsets are known.  The 8 KiB tile limits residency to
-//    3 CTAs per SM, but each value is touched once (a second encode pass costs ~850 warp-instructions per f64 vector).
-//  * TWO PASSES (f32): pass 1 analyses without staging anything; after the CTA's aggregate is published, pass 2 re-reads
-//    the vector (L2), re-encodes it and FFORs into a 4.4 KiB per-warp stage while the scanner works out the offsets;
-//    the stage then leaves with one bulk-async store.  Small footprint -> 4 CTAs per SM, and the wait is overlapped.
+// ORDERED = true  (alpb200_encode_*): blocks and exceptions land in VECTOR ORDER — the bytes of a column are a pure function
+//                  of its values, any vector range is one contiguous byte range.  Price: a block's CTA waits until every
+//                  predecessor has published its size (measured: 25-30 % of the kernel on B200).
+// ORDERED = false (alpb200_encode_unordered_*): one atomicAdd hands out the space, so blocks land in COMPLETION order:
+//                  the same blocks, the same records (offsets differ), dense, but not sorted by vector.
+//
+// ALPB200_ENC_F32_TWO_PASS=1 selects the previous f32 strategy (kept for comparison): pass 1 analyses from global
+// memory without staging, pass 2 re-reads the vector (L2), re-encodes and FFORs into a per-warp stage.
+#ifndef ALPB200_ENC_F32_TWO_PASS
+#define ALPB200_ENC_F32_TWO_PASS 0
+#endif
+#ifndef ALPB200_ENC_SPIN_NS
+#define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth)
+#endif
 template <typename PT>
 struct EncodeCfg;
 template <>
 struct EncodeCfg<double> {
-	static constexpr bool     TWO_PASS       = false;
-	static constexpr uint32_t SMEM_PER_WARP  = VEC * sizeof(double);  // the tile
-	static constexpr uint32_t STAGE_UNITS    = 0;
-	static constexpr int      MIN_BLOCKS     = 3;
+	static constexpr bool     TWO_PASS      = false;
+	static constexpr uint32_t SMEM_PER_WARP = VEC * sizeof(double);  // the tile
+	static constexpr uint32_t INPLACE_MAX   = 32;                    // widest block packed in place
+	static constexpr int      MIN_BLOCKS    = 3;
 };
 template <>
 struct EncodeCfg<float> {
-	static constexpr bool     TWO_PASS       = true;
-	static constexpr uint32_t STAGE_UNITS    = 35;  // every f32 block fits: 32 bits, or ALP_RD 31 + 3
-	static constexpr uint32_t SMEM_PER_WARP  = STAGE_UNITS * 128u;
-	static constexpr int      MIN_BLOCKS     = 4;
+	static constexpr bool     TWO_PASS      = ALPB200_ENC_F32_TWO_PASS != 0;
+	static constexpr uint32_t SMEM_PER_WARP = 35 * 128u;  // tile (32 units); every f32 block fits: 32 bits, or ALP_RD 31 + 3
+	static constexpr uint32_t INPLACE_MAX   = 32;
+	static constexpr int      MIN_BLOCKS    = 4;
 };
 
-template <typename PT, int WARPS>
+template <typename PT, int WARPS, bool ORDERED>
 __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
                                                                                     const alpb200_rg_state* __restrict__ states,
                                                                                     ColOut col, uint64_t* workspace) {
@@ -612,7 +729,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t s_bid;
 	__shared__ uint32_t s_units[WARPS], s_cnt[WARPS];
-	__shared__ uint64_t s_excl;
+	__shared__ uint64_t s_excl, s_pre[WARPS];
 	__shared__ __align__(8) uint64_t s_bar[WARPS];
 
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
@@ -621,7 +738,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_
 	const uint32_t bid    = s_bid;
 	const uint64_t v      = (uint64_t)bid * WARPS + warp;
 	const bool     active = v < n_vectors;
-	uint8_t*       mine   = smem + (size_t)warp * Cfg::SMEM_PER_WARP;  // f64: the tile;  f32: the packed-block stage
+	uint8_t*       mine   = smem + (size_t)warp * Cfg::SMEM_PER_WARP;  // the tile (two-pass f32: the packed-block stage)
 	UT*            tile   = reinterpret_cast<UT*>(mine);
 
 	Analysis<PT> a;
@@ -677,59 +794,80 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_
 		if (t < WARPS) { mine_agg = ((uint64_t)s_units[t] << 32) | s_cnt[t]; }
 		agg                 = warp_sum_u64(mine_agg);
 		const uint32_t wide = __reduce_max_sync(FULL, (uint32_t)(mine_agg >> 32));
+		uint64_t       incl = mine_agg;  // offsets of the warps inside the block
+#pragma unroll
+		for (int d = 1; d < WARPS; d <<= 1) {
+			const uint64_t o = shfl_up_u64(incl, d);
+			if (t >= d) { incl += o; }
+		}
+		if (t < WARPS) { s_pre[t] = incl - mine_agg; }
 		if (t == 0) {
-			st_volatile_u64(&aggregates[bid], SCAN_VALID | agg);
+			if constexpr (ORDERED) { st_volatile_u64(&aggregates[bid], SCAN_VALID | agg); }
 			atomicMax(reinterpret_cast<unsigned long long*>(&col.totals[3]), (unsigned long long)wide * 128ull);
 		}
 	}
 	const uint32_t bytes = units * 128u;
+	// ---- step 4: build the packed block image in shared memory while the scanner works out this block's offsets ----
+	bool staged = false;  // warp-uniform: the block sits at `mine`, ready for a bulk store
 	if constexpr (Cfg::TWO_PASS) {
-		// pass 2: pack into the stage while the scanner works out this block's offsets
 		if (active) {
 			pack_from_input(in_vec, a.bw, a.e, a.f, (UT)a.base, (UT)a.fill, a.myexc, rd, t, mine);
 			if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(mine + 128u * a.bw), PT()); }
-			fence_proxy_async_smem();  // generic-proxy writes to the stage -> visible to the bulk-copy engine
+			staged = true;
+		}
+	} else {
+		if (active && a.bw <= Cfg::INPLACE_MAX) {
+			__syncwarp();  // the tile is complete (analysis stored to it lane by lane)
+			pack_rows_inplace(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t);
+			if (rd) {  // only 32-bit lanes get here: the index block follows the right parts
+				__syncwarp();
+				pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(mine + 128u * a.bw), PT());
+			}
+			staged = true;
 		}
 	}
+	if (staged) { fence_proxy_async_smem(); }  // generic-proxy writes to the block image -> visible to the bulk-copy engine
 	if (warp == 0 && t == 0) {
 		// (a self-service look-back over the 128 nearest predecessors was tried here: one L2 round trip instead of
 		// three, but ~450 spinning blocks x 2 KiB per round put ~1 TB/s of extra traffic on L2 and the kernel got slower)
 		uint64_t excl = 0;
-		if (bid != 0) {
-			while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) {}
+		if constexpr (!ORDERED) {
+			// completion order: one atomic hands out the block's space; the running totals are the column totals
+			excl = (uint64_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace + 1), (unsigned long long)agg);
+			atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[0]), (unsigned long long)(agg >> 32) * 128ull);
+			atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & 0xFFFFFFFFull));
+		} else if (bid != 0) {
+			while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { __nanosleep(ALPB200_ENC_SPIN_NS); }
 			excl &= SCAN_VAL;
 		}
 		s_excl = excl;
-		if ((uint64_t)(bid + 1) * WARPS >= n_vectors) {  // last block: publish the column totals
+		if (ORDERED && (uint64_t)(bid + 1) * WARPS >= n_vectors) {  // last block: publish the column totals
 			const uint64_t incl = excl + agg;
 			col.totals[0]       = (incl >> 32) * 128ull;
 			col.totals[1]       = incl & 0xFFFFFFFFull;
 		}
 	}
 	__syncthreads();
-	const bool scanner = bid == 0 && warp == WARPS - 1;  // this warp produces every block's prefix once its own work is done
+	const bool scanner = ORDERED && bid == 0 && warp == WARPS - 1;  // this warp produces every block's prefix once its own work is done
 	if (!active) {
 		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t); }
 		return;
 	}
-	uint64_t units_off = s_excl >> 32, exc_off = s_excl & 0xFFFFFFFFull;
-	for (int w = 0; w < warp; w++) {
-		units_off += s_units[w];
-		exc_off += s_cnt[w];
-	}
+	const uint64_t my_excl   = s_excl + s_pre[warp];  // both halves add without carry into each other (sizes checked below)
+	const uint64_t units_off = my_excl >> 32, exc_off = my_excl & 0xFFFFFFFFull;
 	if (units_off * 128ull + bytes > col.packed_capacity || exc_off + a.cnt > col.exc_capacity) {
 		if (t == 0) { atomicExch(reinterpret_cast<unsigned long long*>(&col.totals[2]), 1ull); }
 		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t); }
 		return;
 	}
 	uint8_t* dst = col.packed + units_off * 128ull;
-	if constexpr (Cfg::TWO_PASS) {
+	if (staged) {
 		if (t == 0 && bytes) {
 			bulk_s2g(dst, mine, bytes);  // one contiguous write of the whole block (TMA 1-D)
 			bulk_commit();
 		}
 	} else {
-		// FFOR from the tile straight into the column (ALP_RD exceptions concern the left parts only)
+		// wide block: FFOR from the tile straight into the column (ALP_RD exceptions concern the left parts only)
 		pack_rows(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t, dst);
 		if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(dst + 128u * a.bw), PT()); }
 	}
@@ -763,9 +901,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_
 		uint4* out = reinterpret_cast<uint4*>(col.meta + v);
 		out[0]     = ra;
 		out[1]     = rb;
-		if constexpr (Cfg::TWO_PASS) {
-			if (bytes) { bulk_wait_all(); }  // the stage must outlive the bulk store
-		}
+		if (staged && bytes) { bulk_wait_all(); }  // the block image must outlive the bulk store
 	}
 	if (scanner) {
 		__syncwarp();

@@ -129,15 +129,27 @@ __device__ __forceinline__ void window_put(uint32_t (&w)[NW], uint32_t x) {
 }
 
 // 64-bit lanes.  produce(R, lo, hi) yields the (unmasked) field of row R::value; dst = the block as 64-bit elements.
-// Words are stored as soon as they are complete (all positions are compile-time), so only a few stay live.
-template <int BW, typename Produce>
-__device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* __restrict__ dst, Produce&& produce) {
+// DEFER = false: words are stored as soon as they are complete (all positions are compile-time), so only a few stay live.
+// DEFER = true : every word stays in registers until all 32 rows have been produced and the whole warp has passed a
+//                __syncwarp() — for packing IN PLACE, where dst aliases the memory that produce() reads (the block
+//                image of one half of a lane overlaps rows the other half has not read yet).
+template <int BW, bool DEFER = false, typename Produce>
+__device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, Produce&& produce) {
 	uint32_t w[BW + 1];
 	// BW even: pair m = words (2m, 2m+1) -> element 16*(half*BW/2 + m) + lane.
 	// BW odd : half 0 owns stream words 0..BW-1, half 1 words BW..2BW-1, so pairs start one word later for half 1:
 	//          pair m = half ? (2m+1, 2m+2) : (2m, 2m+1) -> element 16*((half ? (BW+1)/2 : 0) + m) + lane, and element
 	//          (BW-1)/2 is shared: last word of half 0 (low) + first word of half 1 (high), completed with one shuffle.
 	uint64_t* p = dst + 16 * ((BW & 1) ? (half ? (BW + 1) / 2 : 0) : half * (BW / 2)) + lane;
+	auto store_pair = [&](auto Mc) {
+		constexpr int m = decltype(Mc)::value;
+		if constexpr ((BW & 1) == 0) {
+			p[16 * m] = (uint64_t)w[2 * m] | ((uint64_t)w[2 * m + 1] << 32);
+		} else {
+			const uint32_t a = half ? w[2 * m + 1] : w[2 * m], b = half ? w[2 * m + 2] : w[2 * m + 1];
+			p[16 * m]        = (uint64_t)a | ((uint64_t)b << 32);
+		}
+	};
 	static_for<0, 32>([&](auto R) {
 		constexpr int r = decltype(R)::value;
 		uint32_t      lo, hi;
@@ -148,19 +160,17 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* __rest
 			window_put<BW + 1, r * BW, 32>(w, lo);
 			window_put<BW + 1, r * BW + 32, BW - 32>(w, hi);
 		}
-		constexpr int done_before = (r * BW) >> 5, done_now = ((r + 1) * BW) >> 5;  // complete words
-		constexpr int pairs_before = (BW & 1) ? (done_before > 0 ? (done_before - 1) / 2 : 0) : done_before / 2;
-		constexpr int pairs_now    = (BW & 1) ? (done_now > 0 ? (done_now - 1) / 2 : 0) : done_now / 2;
-		static_for<pairs_before, pairs_now>([&](auto Mc) {
-			constexpr int m = decltype(Mc)::value;
-			if constexpr ((BW & 1) == 0) {
-				p[16 * m] = (uint64_t)w[2 * m] | ((uint64_t)w[2 * m + 1] << 32);
-			} else {
-				const uint32_t a = half ? w[2 * m + 1] : w[2 * m], b = half ? w[2 * m + 2] : w[2 * m + 1];
-				p[16 * m]        = (uint64_t)a | ((uint64_t)b << 32);
-			}
-		});
+		if constexpr (!DEFER) {
+			constexpr int done_before = (r * BW) >> 5, done_now = ((r + 1) * BW) >> 5;  // complete words
+			constexpr int pairs_before = (BW & 1) ? (done_before > 0 ? (done_before - 1) / 2 : 0) : done_before / 2;
+			constexpr int pairs_now    = (BW & 1) ? (done_now > 0 ? (done_now - 1) / 2 : 0) : done_now / 2;
+			static_for<pairs_before, pairs_now>(store_pair);
+		}
 	});
+	if constexpr (DEFER) {
+		__syncwarp();  // every lane has read all of its rows
+		static_for<0, (BW & 1) ? (BW - 1) / 2 : BW / 2>(store_pair);
+	}
 	if constexpr (BW & 1) {
 		const uint32_t other = __shfl_xor_sync(FULL, half ? w[0] : w[BW - 1], 16);
 		if (half) { dst[16 * ((BW - 1) / 2) + lane] = (uint64_t)other | ((uint64_t)w[0] << 32); }
@@ -168,8 +178,10 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* __rest
 }
 
 // 32-bit lanes.  produce(R) yields the (unmasked) field of row R::value; word i of lane t goes to element 32*i + t.
+// Safe IN PLACE (dst aliasing a [row][lane] tile that produce() reads): word i is complete only after row i has been
+// produced, and element 32*i + t is the slot of this very thread's row i.
 template <int BW, typename Produce>
-__device__ __forceinline__ void pack32_rows(int t, uint32_t* __restrict__ dst, Produce&& produce) {
+__device__ __forceinline__ void pack32_rows(int t, uint32_t* dst, Produce&& produce) {
 	uint32_t w[BW + 1];
 	static_for<0, 32>([&](auto R) {
 		constexpr int r = decltype(R)::value;

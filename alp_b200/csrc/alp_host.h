@@ -43,8 +43,14 @@ template <typename PT>
 int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_out, void* stream);
 template <typename PT>
 int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream);
+template <typename PT, bool ORDERED>
+int launch_encode_impl(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream);
+// ordered = true: blocks in vector order (alpb200_encode_*); false: completion order (alpb200_encode_unordered_*)
 template <typename PT>
-int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream);
+inline int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
+                         bool ordered = true) {
+	return ordered ? launch_encode_impl<PT, true>(d_in, n, d_states, col, ws, stream) : launch_encode_impl<PT, false>(d_in, n, d_states, col, ws, stream);
+}
 template <typename PT>
 int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream);
 template <typename PT>

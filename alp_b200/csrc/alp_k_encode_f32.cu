@@ -1,6 +1,6 @@
-// alp_k_encode_f32.cu — encode_kernel<float> (one translation unit of libalp_b200.so)
+// alp_k_encode_f32.cu — encode_kernel<float, true> (vector-order layout); one translation unit of libalp_b200.so
 #include "alp_k_encode.inc"
 
 namespace alpb200 {
-template int launch_encode<float>(const float*, uint64_t, const alpb200_rg_state*, const alpb200_column*, void*, void*);
+template int launch_encode_impl<float, true>(const float*, uint64_t, const alpb200_rg_state*, const alpb200_column*, void*, void*);
 }

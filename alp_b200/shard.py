@@ -47,15 +47,19 @@ def _u32(meta, byte):
 
 def slice_column(col, first, count):
     """Cut vectors [first, first+count) out of a column given as a dict of tensors
-    {meta uint8 [n,32], packed uint8, exc_val, exc_pos int16} and rebase the offsets in the metadata records."""
+    {meta uint8 [n,32], packed uint8, exc_val, exc_pos int16} and rebase the offsets in the metadata records.
+
+    The byte range is the min / max over the records of the range: for a vector-order column that is exactly the
+    range's own bytes; for a completion-order column (encode(ordered=False)) it also carries the few foreign blocks
+    that finished in between — harmless, the shard's records never point at them."""
     meta = col["meta"][first : first + count].clone()
     if count == 0:
         return {"meta": meta, "packed": col["packed"][:0].clone(), "exc_val": col["exc_val"][:0].clone(), "exc_pos": col["exc_pos"][:0].clone()}
     poff, eoff = _u32(meta, 16), _u32(meta, 20)
     cnt = meta[:, 24:26].contiguous().view(torch.int16).to(torch.int64).reshape(-1) & 0xFFFF
-    p0, e0 = int(poff[0]), int(eoff[0])
-    p1 = int(poff[-1] + _units(meta)[-1])
-    e1 = int(eoff[-1] + cnt[-1])
+    p0, e0 = int(poff.min()), int(eoff.min())
+    p1 = int((poff + _units(meta)).max())
+    e1 = int((eoff + cnt).max())
     meta[:, 16:20] = (poff - p0).to(torch.int32).view(torch.uint8).reshape(-1, 4)
     meta[:, 20:24] = (eoff - e0).to(torch.int32).view(torch.uint8).reshape(-1, 4)
     return {

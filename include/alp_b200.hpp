@@ -33,9 +33,15 @@
 #ifndef ALP_B200_HPP
 #define ALP_B200_HPP
 
+// (the standard headers the reference's headers pull in — code written against alp.hpp relies on them transitively)
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <list>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>

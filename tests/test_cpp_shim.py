@@ -63,3 +63,41 @@ def test_reference_style_program_round_trips_every_fixture(tmp_path, golden_vect
     res = subprocess.run([exe, cases], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "cases %d bad 0" % n in res.stdout
+
+
+# ---- the reference's OWN unit test, unchanged, against the shim -----------------------------------------------------
+REF_TEST = os.path.join(ROOT, "oracle", "_ref", "ref_test_on_shim")
+FIXTURE_ROOT = "/tmp/alp_b200_ref_fixtures"  # baked into the binary as ALP_CMAKE_SOURCE_DIR (oracle/Makefile)
+
+
+def _materialise_reference_fixtures(golden_vectors):
+    """Recreate data/<dir>/<file>.csv of the reference tree from the golden inputs (first 1024 values of each column,
+    all the reference's test reads), written so that std::stod / std::stof give back the exact values."""
+    g = golden_vectors
+    done = {}
+    for c in sorted(g.index, key=lambda c: c["dtype"] != "float64"):  # a file shared by a double and a float case: the double text
+        path = os.path.join(FIXTURE_ROOT, c["relpath"])
+        if path in done:
+            continue
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        x = g[c["id"] + "_input"]
+        with open(path, "w") as fh:
+            for v in x:
+                fh.write((repr(float(v)) if x.dtype == np.float64 else str(v)) + "\n")
+        done[path] = c["id"]
+    return len(done)
+
+
+@pytest.mark.gpu
+def test_reference_own_unit_test_passes_on_the_shim(golden_vectors):
+    """test/test_alp_sample.cpp of the reference — compiled where it lies, not a line changed — linked against
+    include/alp_b200.hpp + libalp_b200.so: its six gtest cases (round trip of 103 columns + the golden bit_width /
+    exceptions_count asserts, :172-179) must pass with every primitive served by the GPU."""
+    if not os.path.exists(REF_TEST):
+        pytest.skip("oracle/_ref/ref_test_on_shim not built (needs /root/reference at build time)")
+    assert _materialise_reference_fixtures(golden_vectors) >= 100
+    res = subprocess.run([REF_TEST], capture_output=True, text=True, timeout=900)
+    tail = res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.returncode == 0, tail
+    assert "[  PASSED  ] 6 tests." in res.stdout, tail
+    assert res.stdout.count("[       OK ]") == 6, tail

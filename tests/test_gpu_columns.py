@@ -183,6 +183,176 @@ def test_edge_shapes(checker):
             _assert_columns_equal(h, want, name)
 
 
+def _width_sweep_column(dtype, widths, rng, n_exceptions=3):
+    """One ROW-GROUP (100 vectors) per bit width w, so that the row-group's (e,f) search sees only that kind of data:
+    integers spanning exactly [0, 2^w - 1] in every vector (FFOR then packs w bits), plus a few NaNs per vector (exceptions)."""
+    mant = 52 if dtype == np.float64 else 23
+    parts = []
+    for w in widths:
+        span = (1 << w) - 1
+        step = 1 if w <= mant else 1 << (w - mant)  # keep every value exactly representable
+        k = rng.integers(0, span // step + 1, size=(100, 1024), dtype=np.uint64)
+        k[:, 0], k[:, 1] = 0, span // step
+        v = (k * np.uint64(step)).astype(dtype)
+        v = rng.permuted(v, axis=1)
+        for row in v:
+            row[rng.choice(1024, size=n_exceptions, replace=False)] = np.nan
+        parts.append(v.reshape(-1))
+    return np.concatenate(parts)
+
+
+# (wider integer columns fall to ALP_RD: the row-group search gives up at 48 / 22 bits, constants.hpp:33,69)
+@pytest.mark.parametrize("dtype,widths", [(np.float64, list(range(0, 48))), (np.float32, list(range(0, 22)))])
+def test_batched_encode_every_bit_width(dtype, widths, checker):
+    """Every FFOR width through the BATCHED kernels (in-place packing + bulk store for narrow blocks, direct line
+    stores for wide ones; the width-specialised unpackers; the integer fast path of the fused SUM): byte-identical to
+    the checker's column, decodable both ways, and per-vector SUM within 1e-12 of the decoded values' sum."""
+    import torch
+
+    import alp_b200
+
+    rng = np.random.default_rng(11)
+    x = _width_sweep_column(dtype, widths, rng)
+    xd = torch.from_numpy(x).to(_dev())
+    col = alp_b200.encode(xd)
+    h = col.to_host()
+    want = checker.encode_column(x, n_threads=8)
+    assert set(want.meta["scheme"].tolist()) == {2}
+    assert sorted(set(want.meta["bw"].tolist())) == widths  # the sweep really covers every width
+    _assert_columns_equal(h, want, "width-sweep")
+    y = alp_b200.decode(col)
+    assert torch.equal(_bits(y), _bits(xd))
+    assert checker.decode_column(h, n_threads=8).tobytes() == x.tobytes()
+    # SUM of one vector per width (NaN exceptions propagate, so compare on a NaN-free copy of the column)
+    clean = np.nan_to_num(x, nan=1.0)
+    cd = torch.from_numpy(clean).to(_dev())
+    ccol = alp_b200.encode(cd)
+    ccol.read_totals()
+    for i, w in enumerate(widths):
+        first = i * 100 + 7
+        v = cd[first * 1024 : (first + 1) * 1024].double()
+        got = float(alp_b200.decode_sum(ccol, first=first, n=1).item())
+        assert abs(got - float(v.sum().item())) <= 1e-12 * max(float(v.abs().sum().item()), 1e-300), (w, got, float(v.sum().item()))
+    total = float(alp_b200.decode_sum(ccol).item())
+    assert abs(total - float(cd.double().sum().item())) <= 1e-12 * float(cd.double().abs().sum().item())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_encode_near_the_integer_overflow_boundaries(dtype, checker):
+    """The encoder's floating-point fast path (alp_encode.cuh, analyze_rows<FAST>) must hand over to the exact recipe
+    wherever enc * 10^f can wrap or the x86 cast semantics matter: decimals whose scaled integer sits right at
+    +-2^63 / 10^f (+-2^31 / 10^f for floats), +-2^63 itself, huge values, infinities and NaNs, mixed into ordinary
+    decimal vectors.  Byte-identical to the checker's column, for several decimal scales."""
+    import torch
+
+    import alp_b200
+
+    rng = np.random.default_rng(5)
+    top = 63 if dtype == np.float64 else 31
+    parts = []
+    for decimals in (0, 1, 2, 3, 5):
+        scale = 10.0**decimals
+        base = np.round(rng.uniform(-5000, 5000, size=(100, 1024)), decimals)
+        for f in range(0, 14 if dtype == np.float64 else 8):
+            # x * 10^decimals * 10^f ~ 2^top: the products enc * 10^f of these land on both sides of the wrap
+            edge = (2.0**top) / (10.0**f) / scale
+            cand = np.array([edge, -edge, np.nextafter(edge, 0), np.nextafter(edge, np.inf), edge * (1 - 1e-7), edge * (1 + 1e-7),
+                             np.floor(edge), np.floor(edge) + 1, -np.floor(edge) - 1, edge / 2, edge * 2, edge * 0.999, edge * 1.001])
+            rows = rng.integers(0, 100, size=cand.size)
+            cols = rng.integers(0, 1024, size=cand.size)
+            base[rows, cols] = cand
+        special = np.array([2.0**top, -(2.0**top), 2.0**top * 1.5, -(2.0**top) * 1.5, 1e30, -1e30, np.inf, -np.inf, np.nan, -0.0, 2.0 ** (top - 1)])
+        base[rng.integers(0, 100, size=special.size), rng.integers(0, 1024, size=special.size)] = special
+        parts.append(base.reshape(-1))
+    with np.errstate(over="ignore"):
+        x = np.concatenate(parts).astype(dtype)
+    xd = torch.from_numpy(x).to(_dev())
+    col = alp_b200.encode(xd)
+    h = col.to_host()
+    want = checker.encode_column(x, n_threads=8)
+    assert 2 in set(want.meta["scheme"].tolist())
+    _assert_columns_equal(h, want, "overflow-boundaries")
+    assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd))
+
+
+def _blocks(h):
+    """per-vector (packed block bytes, exception values, exception positions) of a HostColumn, whatever its layout"""
+    m = h.meta[: h.n_vectors]
+    units = np.where(m["scheme"] == 1, m["bw"].astype(np.int64) + m["e"].astype(np.int64), m["bw"].astype(np.int64))
+    out = []
+    for v in range(h.n_vectors):
+        p, e, c = int(m["packed_off"][v]) * 128, int(m["exc_off"][v]), int(m["exc_cnt"][v])
+        out.append((h.packed[p : p + int(units[v]) * 128].tobytes(), h.exc_val[e : e + c].tobytes(), h.exc_pos[e : e + c].tobytes()))
+    return out, units
+
+
+@pytest.mark.parametrize("kind", [2, 3, 4])
+def test_completion_order_layout(kind, checker):
+    """alpb200_encode_unordered_*: the same per-vector blocks, exception runs and record fields as the vector-order
+    encoder (hence as the checker), dense (blocks tile [0, total) without gaps or overlaps), decodable by the GPU, by the
+    CPU checker, through the host-buffer API, and shardable."""
+    import torch
+
+    import alp_b200
+    from alp_b200 import shard
+    from oracle import pyoracle
+
+    n = 7 * 102400 + 31 * 1024
+    x = pyoracle.generate(n, kind)
+    xd = torch.from_numpy(x).to(_dev())
+    ordered = alp_b200.encode(xd).to_host()
+    col = alp_b200.encode(xd, ordered=False)
+    h = col.to_host()
+    assert (h.packed_bytes, h.n_exceptions) == (ordered.packed_bytes, ordered.n_exceptions)
+    for key in ("exc_cnt", "scheme", "bw", "e", "f"):
+        assert np.array_equal(h.meta[key], ordered.meta[key]), key
+    got, units = _blocks(h)
+    want, _ = _blocks(ordered)
+    assert got == want
+    # dense: sorted by offset, every non-empty block / exception run starts where the previous one ends
+    def tiles(offsets, sizes, total):
+        keep = sizes > 0
+        off, sz = offsets[keep].astype(np.int64), sizes[keep].astype(np.int64)
+        order = np.argsort(off)
+        off, sz = off[order], sz[order]
+        return off.size == 0 or (off[0] == 0 and np.array_equal(off[1:], (off + sz)[:-1]) and int(off[-1] + sz[-1]) == total)
+
+    assert tiles(h.meta["packed_off"], units, h.packed_bytes // 128)
+    assert tiles(h.meta["exc_off"], h.meta["exc_cnt"].astype(np.int64), h.n_exceptions)
+    # decodable everywhere
+    assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd))
+    assert checker.decode_column(h, n_threads=4).tobytes() == x.tobytes()
+    got_sum = float(alp_b200.decode_sum(col).item())
+    want_sum = float(xd.double().sum().item())
+    assert abs(got_sum - want_sum) <= 1e-9 * max(1.0, abs(want_sum))
+    # host-buffer API with the option set: compress -> decompress / sum
+    codec = alp_b200.HostCodec(n // 1024, x.dtype.itemsize, ordered=False)
+    hc = codec.compress(x)
+    assert codec.decompress(hc).tobytes() == x.tobytes()
+    assert abs(codec.sum(hc) - want_sum) <= 1e-9 * max(1.0, abs(want_sum))
+    codec.close()
+    # a shard cut out of it decodes on its own
+    t = shard.column_tensors(col)
+    s = shard.slice_column(t, 200, 300)
+    sc = shard.tensors_to_device_column(s, x.dtype.itemsize, _dev())
+    assert torch.equal(_bits(alp_b200.decode(sc)), _bits(xd[200 * 1024 : 500 * 1024]))
+
+
+def test_host_decompress_of_a_shuffled_column(checker):
+    """decompress_host / sum_host make no assumption about block order: a column whose blocks were permuted at random."""
+    import alp_b200
+    from conftest import shuffle_layout
+    from oracle import pyoracle
+
+    n = 40 * 102400
+    x = pyoracle.generate(n, 2)
+    shuffled = shuffle_layout(checker.encode_column(x, n_threads=8), np.random.default_rng(4))
+    codec = alp_b200.HostCodec(n // 1024, 8)
+    assert codec.decompress(shuffled).tobytes() == x.tobytes()
+    assert abs(codec.sum(shuffled) - float(x.sum())) <= 1e-12 * float(np.abs(x).sum())
+    codec.close()
+
+
 def test_capacity_overflow_is_reported():
     import torch
 
@@ -283,6 +453,23 @@ def test_fused_decode_sum_propagates_nan():
     col = alp_b200.encode(x)
     col.read_totals()
     assert torch.isnan(alp_b200.decode_sum(col)).item()
+
+
+@pytest.mark.parametrize("kind,n_extra", [(2, 0), (2, 777), (3, 0), (4, 5)])
+def test_host_codec_sum(kind, n_extra):
+    """alpb200_sum_host_*: SUM of a HOST column container (only compressed bytes cross PCIe, one double comes back),
+    with and without a padded tail vector; relative 1e-12 against numpy's float64 sum of the original values."""
+    import alp_b200
+    from oracle import pyoracle
+
+    n = 3 * 102400 + 17 * 1024 + n_extra
+    x = pyoracle.generate(n + 1024, kind)[:n].copy()
+    codec = alp_b200.HostCodec(n // 1024 + 1, x.dtype.itemsize)
+    col = codec.compress(x)
+    got = codec.sum(col)
+    want = float(np.sum(x.astype(np.float64)))
+    assert abs(got - want) <= 1e-12 * float(np.sum(np.abs(x.astype(np.float64)))), (got, want)
+    codec.close()
 
 
 @pytest.mark.parametrize("n_tail", [1, 777, 1023])

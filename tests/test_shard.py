@@ -92,3 +92,21 @@ def test_slice_column_rebases_offsets(port):
         assert h.n_vectors == count
         if count:
             assert port.decode_column(h).tobytes() == x[first * 1024 : (first + count) * 1024].tobytes()
+
+
+def test_slice_column_of_a_completion_order_layout(port):
+    """Shards of a column whose blocks are NOT in vector order (alpb200_encode_unordered_*; here: a random permutation of
+    an ordered column's blocks) still decode on their own: slice_column takes the min/max byte range of the records."""
+    from conftest import shuffle_layout
+
+    from alp_b200 import shard
+    from oracle import pyoracle
+
+    x = np.concatenate([pyoracle.generate(102400, 2), pyoracle.generate(102400, 3), pyoracle.generate(30 * 1024, 2, first_index=5)])
+    shuffled = shuffle_layout(port.encode_column(x), np.random.default_rng(9))
+    assert port.decode_column(shuffled).tobytes() == x.tobytes()
+    t = shard.host_column_tensors(shuffled)
+    for first, count in ((0, 100), (100, 100), (37, 120), (229, 1), (0, 230)):
+        s = shard.slice_column(t, first, count)
+        h = shard.tensors_to_host_column(s, 8)
+        assert port.decode_column(h).tobytes() == x[first * 1024 : (first + count) * 1024].tobytes()

@@ -88,6 +88,7 @@ def main():
                 group=group,
                 name=row["name"],
                 file=os.path.basename(row["csv"]),
+                relpath=os.path.relpath(row["csv"], REF),  # where the reference's own test looks for it (under ALP_CMAKE_SOURCE_DIR)
                 dtype=np.dtype(dtype).name,
                 golden_bw=row["golden_bw"],
                 golden_exceptions=row["golden_exceptions"],
