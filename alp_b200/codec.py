@@ -89,9 +89,10 @@ class DeviceColumn:
         if n == 0:
             return _abi.HostColumn(0, self.value_bytes, 128, 1)
         units = np.where(meta["scheme"] == _abi.SCHEME_ALP_RD, meta["bw"].astype(np.int64) + meta["e"], meta["bw"].astype(np.int64))
-        p0, e0 = int(meta["packed_off"][0]) * 128, int(meta["exc_off"][0])
-        p1 = (int(meta["packed_off"][-1]) + int(units[-1])) * 128
-        e1 = int(meta["exc_off"][-1]) + int(meta["exc_cnt"][-1])
+        # min / max over the records: exact for a vector-order column, a slight superset for a completion-order one
+        p0, e0 = int(meta["packed_off"].min()) * 128, int(meta["exc_off"].min())
+        p1 = int((meta["packed_off"].astype(np.int64) + units).max()) * 128
+        e1 = int((meta["exc_off"].astype(np.int64) + meta["exc_cnt"]).max())
         h = _abi.HostColumn(n, self.value_bytes, max(p1 - p0, 128), max(e1 - e0, 1))
         meta["packed_off"] -= p0 // 128
         meta["exc_off"] -= e0

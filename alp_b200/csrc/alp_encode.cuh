@@ -368,20 +368,24 @@ __device__ __forceinline__ void analyze_rd(const alpb200_rg_state* state, const 
 	const uint32_t lmask = (1u << lbw) - 1;
 	uint32_t       myexc = 0;
 	uint32_t       nib0 = 0, nib1 = 0, nib2 = 0, nib3 = 0;
+	// the dictionary as eight 32-bit compare operands; slots beyond dict_size can never match (left parts are < 2^16)
+	uint32_t dict[ALPB200_RD_DICT_SIZE];
+#pragma unroll
+	for (uint32_t d = 0; d < ALPB200_RD_DICT_SIZE; d++) {
+		dict[d] = d < ds ? dict_lookup(st.dict, d) : 0xFFFFFFFFu;
+	}
 	static_for<0, 32>([&](auto R) {
 		constexpr int  r    = decltype(R)::value;
 		const UT       bits = io.load(R);
 		const uint32_t left = (uint32_t)(bits >> rbw);
 		io.store(R, bits & rmask);
 		uint32_t idx = ds;  // rd.hpp:129-131: a left part nobody has seen gets the smallest non-dictionary index
-		bool     hit = false;
+		// (entries are distinct — rd.hpp:56-66 takes them from a map's keys; descending, so that the lowest slot would win)
 #pragma unroll
-		for (uint32_t d = 0; d < ALPB200_RD_DICT_SIZE; d++) {
-			if (d < ds && !hit && dict_lookup(st.dict, d) == left) {
-				idx = d;
-				hit = true;
-			}
+		for (int d = ALPB200_RD_DICT_SIZE - 1; d >= 0; d--) {
+			idx = left == dict[d] ? (uint32_t)d : idx;
 		}
+		const bool hit = idx != ds;
 		if (st.n_extra != 0 && !hit) {  // rd.hpp:73-77,133: sampled left parts outside the dictionary
 			for (uint32_t x = 0; x < st.n_extra; x++) {
 				if (state->extra_key[x] == left) {
@@ -699,6 +703,9 @@ struct ColOut {
 #ifndef ALPB200_ENC_F32_TWO_PASS
 #define ALPB200_ENC_F32_TWO_PASS 0
 #endif
+#ifndef ALPB200_ENC_LOOKBACK
+#define ALPB200_ENC_LOOKBACK 1  // 1: blocks resolve their prefix themselves from a 32-wide window when they can (see the kernel)
+#endif
 #ifndef ALPB200_ENC_SPIN_NS
 #define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth)
 #endif
@@ -827,24 +834,54 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_
 		}
 	}
 	if (staged) { fence_proxy_async_smem(); }  // generic-proxy writes to the block image -> visible to the bulk-copy engine
-	if (warp == 0 && t == 0) {
-		// (a self-service look-back over the 128 nearest predecessors was tried here: one L2 round trip instead of
-		// three, but ~450 spinning blocks x 2 KiB per round put ~1 TB/s of extra traffic on L2 and the kernel got slower)
+	if (warp == 0) {
 		uint64_t excl = 0;
 		if constexpr (!ORDERED) {
 			// completion order: one atomic hands out the block's space; the running totals are the column totals
-			excl = (uint64_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace + 1), (unsigned long long)agg);
-			atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[0]), (unsigned long long)(agg >> 32) * 128ull);
-			atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & 0xFFFFFFFFull));
+			if (t == 0) {
+				excl = (uint64_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace + 1), (unsigned long long)agg);
+				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[0]), (unsigned long long)(agg >> 32) * 128ull);
+				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & 0xFFFFFFFFull));
+			}
 		} else if (bid != 0) {
-			while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { __nanosleep(ALPB200_ENC_SPIN_NS); }
-			excl &= SCAN_VAL;
+#if ALPB200_ENC_LOOKBACK
+			// Short look-back next to the scanner.  Lane l reads the prefix of block bid-l and the aggregate of block
+			// bid-1-l (two 256-byte segments per poll).  If some prefix in the window is known and every aggregate between
+			// it and this block is published, the block's own prefix follows at once — one L2 round trip after the last
+			// predecessor published instead of three (aggregate -> scanner -> prefix -> here) — and is published for the
+			// successors.  The scanner still guarantees progress when more than 32 blocks queue up behind a straggler.
+			// (An earlier 128-wide version without back-off put ~1 TB/s of polling on L2 and lost; this one polls 512 B.)
+			const int64_t pi = (int64_t)bid - t, ai = (int64_t)bid - 1 - t;
+			for (;;) {
+				const uint64_t P  = pi > 0 ? ld_volatile_u64(&prefixes[pi]) : (pi == 0 ? SCAN_VALID : 0ull);
+				const uint64_t A  = ai >= 0 ? ld_volatile_u64(&aggregates[ai]) : 0ull;
+				const uint32_t vp = __ballot_sync(FULL, (P & SCAN_VALID) != 0);
+				const uint32_t va = __ballot_sync(FULL, (A & SCAN_VALID) != 0);
+				const uint32_t n_a   = va == FULL ? 32u : (uint32_t)__ffs((int)~va) - 1u;  // leading published aggregates
+				const uint32_t reach = n_a >= 31 ? FULL : ((2u << n_a) - 1u);              // prefixes of blocks bid .. bid-n_a
+				const uint32_t cand  = vp & reach;
+				if (cand) {
+					const int l = __ffs((int)cand) - 1;
+					excl        = (shfl_u64(P, l) & SCAN_VAL) + warp_sum_u64(t < l ? (A & SCAN_VAL) : 0ull);
+					if (l > 0 && t == 0) { st_volatile_u64(&prefixes[bid], SCAN_VALID | excl); }
+					break;
+				}
+				__nanosleep(ALPB200_ENC_SPIN_NS);
+			}
+#else
+			if (t == 0) {
+				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { __nanosleep(ALPB200_ENC_SPIN_NS); }
+				excl &= SCAN_VAL;
+			}
+#endif
 		}
-		s_excl = excl;
-		if (ORDERED && (uint64_t)(bid + 1) * WARPS >= n_vectors) {  // last block: publish the column totals
-			const uint64_t incl = excl + agg;
-			col.totals[0]       = (incl >> 32) * 128ull;
-			col.totals[1]       = incl & 0xFFFFFFFFull;
+		if (t == 0) {
+			s_excl = excl;
+			if (ORDERED && (uint64_t)(bid + 1) * WARPS >= n_vectors) {  // last block: publish the column totals
+				const uint64_t incl = excl + agg;
+				col.totals[0]       = (incl >> 32) * 128ull;
+				col.totals[1]       = incl & 0xFFFFFFFFull;
+			}
 		}
 	}
 	__syncthreads();

@@ -243,19 +243,23 @@ def main():
 
     # ---- untimed set-up: this rank's shard of the global column, compressed on the device ----
     x = alp_b200.generate(n, KIND, dev, first_index=rank * n)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     big = alp_b200.DeviceColumn(n_vec, 8, dev)  # worst-case capacities; allocated before anything is timed
     ws = torch.empty(max(256, alp_b200.lib.alpb200_encode_workspace_bytes(n_vec)), dtype=torch.uint8, device=dev)
     states = alp_b200.rowgroup_init(x)
     alp_b200.encode(x, states, col=big, workspace=ws)  # warm-up pass (also first touch of the output buffers)
+    alp_b200.encode(x, states, col=big, workspace=ws, ordered=False)
     torch.cuda.synchronize()
+    ev[3].record()
+    alp_b200.encode(x, states, col=big, workspace=ws, ordered=False)  # completion-order layout (reported beside the default)
+    ev[4].record()
     ev[0].record()
     states = alp_b200.rowgroup_init(x)
     ev[1].record()
-    alp_b200.encode(x, states, col=big, workspace=ws)
+    alp_b200.encode(x, states, col=big, workspace=ws)  # the default, vector-order layout: this is the column decoded below
     ev[2].record()
     packed_bytes, n_exc = big.read_totals()
-    init_ms, encode_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    init_ms, encode_ms, encode_unordered_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[3].elapsed_time(ev[4])
     # trim the worst-case container to what was used
     col = alp_b200.DeviceColumn(n_vec, 8, dev, max(packed_bytes, 128), max(n_exc, 1))
     col.meta.copy_(big.meta)
@@ -305,8 +309,21 @@ def main():
     # encode side (reported, not the headline): device-timed, input resident
     enc_gbps = n * 8.0 / (encode_ms * 1e-3) / 1e9
 
+    # fused decode + SUM scan (reported, not the headline): nothing is written back, so the bound is the compressed read
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        alp_b200.decode_sum(col, out=acc)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        alp_b200.decode_sum(col, out=acc)
+    s1.record()
+    torch.cuda.synchronize()
+    scan_ms = s0.elapsed_time(s1) / args.steps
+
     # ---- e2e: host column in, host values out, through alpb200_decompress_host ----
-    e2e = None
+    e2e = e2e_scan = None
     if not args.no_e2e:
         hcol = pinned_host_column(col.to_host())
         hout_t = torch.empty(n, dtype=torch.float64, pin_memory=True)
@@ -332,6 +349,27 @@ def main():
             "ms_per_step": e2e_s * 1e3,
             "steps": args.e2e_steps,
             "api": "alpb200_decompress_host_f64 (pinned host buffers, 16-chunk pipeline over 3 streams)",
+        }
+        # the scan query end to end: host column in, one double out (only the compressed bytes cross PCIe)
+        want_sum = float(x.sum().item())
+        got_sum = codec.sum(hcol)
+        assert abs(got_sum - want_sum) <= 1e-9 * abs(want_sum), (got_sum, want_sum)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            codec.sum(hcol)
+        scan_s = (time.perf_counter() - t0) / args.e2e_steps
+        ts = torch.tensor([scan_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        scan_s = float(ts.item())
+        e2e_scan = {
+            "value": world * n * 8.0 / scan_s / 1e9,
+            "unit": "GB/s of decoded-equivalent f64 scanned",
+            "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": 8,
+            "ms_per_step": scan_s * 1e3,
+            "api": "alpb200_sum_host_f64 (SUM over the host column; reference: bench_end_to_end alp_func + aggr_plus)",
         }
         codec.close()
 
@@ -399,7 +437,22 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks.summary(),
-            "encode": {"GBps": enc_gbps, "ms": encode_ms, "rowgroup_init_ms": init_ms, "bits_per_value": 8.0 * read_bytes / n},
+            "e2e_scan": e2e_scan,
+            "encode": {
+                "GBps": enc_gbps,
+                "ms": encode_ms,
+                "roofline_frac": algo_bytes / (encode_ms * 1e-3) / 1e9 / peak,
+                "rowgroup_init_ms": init_ms,
+                "bits_per_value": 8.0 * read_bytes / n,
+                "unordered_layout": {"GBps": n * 8.0 / (encode_unordered_ms * 1e-3) / 1e9, "ms": encode_unordered_ms,
+                                     "roofline_frac": algo_bytes / (encode_unordered_ms * 1e-3) / 1e9 / peak},
+            },
+            "scan_sum": {
+                "ms": scan_ms,
+                "GBps_decoded_equivalent": n * 8.0 / (scan_ms * 1e-3) / 1e9,
+                "read_GBps": read_bytes / (scan_ms * 1e-3) / 1e9,
+                "roofline_frac": read_bytes / (scan_ms * 1e-3) / 1e9 / peak,
+            },
         }
         print(json.dumps(line))
     if world > 1:

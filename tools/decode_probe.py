@@ -52,11 +52,12 @@ def main():
         ms = timed(lambda: alp_b200.decode(col, out=out))
         enc_ws = torch.empty(max(256, alp_b200.lib.alpb200_encode_workspace_bytes(col.n_vectors)), dtype=torch.uint8, device=dev)
         st = alp_b200.rowgroup_init(x)
+        ums = timed(lambda: alp_b200.encode(x, st, col=col, workspace=enc_ws, ordered=False), 3) if hasattr(alp_b200.lib, "alpb200_encode_unordered_f64") else float("nan")
         ems = timed(lambda: alp_b200.encode(x, st, col=col, workspace=enc_ws), 3)
         acc = torch.zeros(1, dtype=torch.float64, device=dev)
         sms = timed(lambda: alp_b200.decode_sum(col, out=acc))
-        print("%-36s ok=%s bits/val=%5.2f exc/vec=%6.1f bw=%s | decode %.3f ms %6.0f GB/s out, %6.0f GB/s algo | encode %.3f ms %6.0f GB/s in | sum-scan %.3f ms %6.0f GB/s decoded-equivalent %5.0f GB/s read" % (
-            name, ok, 8.0 * read / n, ne / col.n_vectors, sorted(set(meta["bw"].tolist()))[:4], ms, n * vb / ms / 1e6, algo / ms / 1e6, ems, n * vb / ems / 1e6, sms, n * vb / sms / 1e6, read / sms / 1e6))
+        print("%-36s ok=%s bits/val=%5.2f exc/vec=%6.1f bw=%s | decode %.3f ms %6.0f GB/s out, %6.0f GB/s algo | encode %.3f ms %6.0f GB/s in (unordered %.3f ms) | sum-scan %.3f ms %6.0f GB/s decoded-equivalent %5.0f GB/s read" % (
+            name, ok, 8.0 * read / n, ne / col.n_vectors, sorted(set(meta["bw"].tolist()))[:4], ms, n * vb / ms / 1e6, algo / ms / 1e6, ems, n * vb / ems / 1e6, ums, sms, n * vb / sms / 1e6, read / sms / 1e6))
         del col, out
 
 

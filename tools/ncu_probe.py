@@ -2,7 +2,7 @@
 """Run ONE hot-path launch a few times, for profiling under ncu (never a bench value).
 
     ncu --set full --import-source on --clock-control none -k regex:encode_kernel -s 1 -c 1 -o gpurun_out/enc \
-        python tools/ncu_probe.py encode 2 27          # what (encode|decode|sum), column kind (2|3|4|int), log2(values)
+        python tools/ncu_probe.py encode 2 27          # what (encode|encode_unordered|decode|sum), column kind (2|3|4|int), log2(values)
 """
 import os
 import sys
@@ -27,10 +27,11 @@ def main():
     ws = torch.empty(max(256, alp_b200.lib.alpb200_encode_workspace_bytes(n // 1024)), dtype=torch.uint8, device=dev)
     out = torch.empty_like(x)
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
-    alp_b200.encode(x, st, col=col, workspace=ws)
+    ordered = what != "encode_unordered"
+    alp_b200.encode(x, st, col=col, workspace=ws, ordered=ordered)
     col.read_totals()  # also learns the widest block: the decoders size their stages from it
     for _ in range(3):
-        alp_b200.encode(x, st, col=col, workspace=ws)
+        alp_b200.encode(x, st, col=col, workspace=ws, ordered=ordered)
         if what == "decode":
             alp_b200.decode(col, out=out)
         if what == "sum":
