@@ -703,9 +703,6 @@ struct ColOut {
 #ifndef ALPB200_ENC_F32_TWO_PASS
 #define ALPB200_ENC_F32_TWO_PASS 0
 #endif
-#ifndef ALPB200_ENC_LOOKBACK
-#define ALPB200_ENC_LOOKBACK 1  // 1: blocks resolve their prefix themselves from a 32-wide window when they can (see the kernel)
-#endif
 #ifndef ALPB200_ENC_SPIN_NS
 #define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth)
 #endif
@@ -716,18 +713,18 @@ struct EncodeCfg<double> {
 	static constexpr bool     TWO_PASS      = false;
 	static constexpr uint32_t SMEM_PER_WARP = VEC * sizeof(double);  // the tile
 	static constexpr uint32_t INPLACE_MAX   = 32;                    // widest block packed in place
-	static constexpr int      MIN_BLOCKS    = 3;
+	static constexpr int      WARPS_PER_SM  = 24;  // 8 KiB of shared memory and 80 registers per thread
 };
 template <>
 struct EncodeCfg<float> {
 	static constexpr bool     TWO_PASS      = ALPB200_ENC_F32_TWO_PASS != 0;
 	static constexpr uint32_t SMEM_PER_WARP = 35 * 128u;  // tile (32 units); every f32 block fits: 32 bits, or ALP_RD 31 + 3
 	static constexpr uint32_t INPLACE_MAX   = 32;
-	static constexpr int      MIN_BLOCKS    = 4;
+	static constexpr int      WARPS_PER_SM  = 32;  // 4.4 KiB and 64 registers
 };
 
 template <typename PT, int WARPS, bool ORDERED>
-__global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
+__global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARPS) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
                                                                                     const alpb200_rg_state* __restrict__ states,
                                                                                     ColOut col, uint64_t* workspace) {
 	using T   = Traits<PT>;
@@ -844,36 +841,13 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::MIN_BLOCKS) encode_
 				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & 0xFFFFFFFFull));
 			}
 		} else if (bid != 0) {
-#if ALPB200_ENC_LOOKBACK
-			// Short look-back next to the scanner.  Lane l reads the prefix of block bid-l and the aggregate of block
-			// bid-1-l (two 256-byte segments per poll).  If some prefix in the window is known and every aggregate between
-			// it and this block is published, the block's own prefix follows at once — one L2 round trip after the last
-			// predecessor published instead of three (aggregate -> scanner -> prefix -> here) — and is published for the
-			// successors.  The scanner still guarantees progress when more than 32 blocks queue up behind a straggler.
-			// (An earlier 128-wide version without back-off put ~1 TB/s of polling on L2 and lost; this one polls 512 B.)
-			const int64_t pi = (int64_t)bid - t, ai = (int64_t)bid - 1 - t;
-			for (;;) {
-				const uint64_t P  = pi > 0 ? ld_volatile_u64(&prefixes[pi]) : (pi == 0 ? SCAN_VALID : 0ull);
-				const uint64_t A  = ai >= 0 ? ld_volatile_u64(&aggregates[ai]) : 0ull;
-				const uint32_t vp = __ballot_sync(FULL, (P & SCAN_VALID) != 0);
-				const uint32_t va = __ballot_sync(FULL, (A & SCAN_VALID) != 0);
-				const uint32_t n_a   = va == FULL ? 32u : (uint32_t)__ffs((int)~va) - 1u;  // leading published aggregates
-				const uint32_t reach = n_a >= 31 ? FULL : ((2u << n_a) - 1u);              // prefixes of blocks bid .. bid-n_a
-				const uint32_t cand  = vp & reach;
-				if (cand) {
-					const int l = __ffs((int)cand) - 1;
-					excl        = (shfl_u64(P, l) & SCAN_VAL) + warp_sum_u64(t < l ? (A & SCAN_VAL) : 0ull);
-					if (l > 0 && t == 0) { st_volatile_u64(&prefixes[bid], SCAN_VALID | excl); }
-					break;
-				}
-				__nanosleep(ALPB200_ENC_SPIN_NS);
-			}
-#else
+			// (Blocks resolving their own prefix from a window of predecessors next to the scanner — one L2 round trip
+			// instead of three — was measured twice and lost both times: 128-wide without back-off, ~1 TB/s of polling on
+			// L2, 4.65 vs 3.9 ms; 32-wide with back-off and all 32 lanes of this warp polling, 1.66 vs 1.52 ms per 2^29.)
 			if (t == 0) {
 				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { __nanosleep(ALPB200_ENC_SPIN_NS); }
 				excl &= SCAN_VAL;
 			}
-#endif
 		}
 		if (t == 0) {
 			s_excl = excl;

@@ -26,7 +26,10 @@ int fail(int code, const char* fmt, const char* a = "", const char* b = "");
 	} while (0)
 
 constexpr int DEC_WARPS = 8;
-constexpr int ENC_WARPS = 8;
+#ifndef ALPB200_ENC_WARPS
+#define ALPB200_ENC_WARPS 8  // vectors (warps) per encode thread block
+#endif
+constexpr int ENC_WARPS = ALPB200_ENC_WARPS;
 
 struct DeviceInfo {
 	int sms        = 0;
