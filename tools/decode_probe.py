@@ -14,6 +14,18 @@ import alp_b200  # noqa: E402
 from alp_b200 import _abi  # noqa: E402
 
 
+def _peak():
+    import json
+
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+PEAK = _peak()  # GB/s, the measured copy bandwidth the roofline fractions refer to
+
+
 def timed(fn, n=5):
     fn()
     torch.cuda.synchronize()
@@ -37,7 +49,7 @@ def main():
     cols["2-decimal<100 f64 (bw 14)"] = torch.randint(0, 10000, (n,), device=dev, generator=g).double() / 100.0
     cols["highprec_f64 (config 3, ALP_RD)"] = alp_b200.generate(n, 3, dev)
     cols["mixed_f32 (config 4)"] = alp_b200.generate(n, 4, dev)
-    print("lib", alp_b200.LIB_PATH)
+    print("lib", alp_b200.LIB_PATH, " values 2^%d  HBM peak %.0f GB/s (MEASURED_PEAKS.json)" % (lg, PEAK))
     for name, x in cols.items():
         vb = x.element_size()
         col = alp_b200.encode(x)
@@ -56,8 +68,9 @@ def main():
         ems = timed(lambda: alp_b200.encode(x, st, col=col, workspace=enc_ws), 3)
         acc = torch.zeros(1, dtype=torch.float64, device=dev)
         sms = timed(lambda: alp_b200.decode_sum(col, out=acc))
-        print("%-36s ok=%s bits/val=%5.2f exc/vec=%6.1f bw=%s | decode %.3f ms %6.0f GB/s out, %6.0f GB/s algo | encode %.3f ms %6.0f GB/s in (unordered %.3f ms) | sum-scan %.3f ms %6.0f GB/s decoded-equivalent %5.0f GB/s read" % (
-            name, ok, 8.0 * read / n, ne / col.n_vectors, sorted(set(meta["bw"].tolist()))[:4], ms, n * vb / ms / 1e6, algo / ms / 1e6, ems, n * vb / ems / 1e6, ums, sms, n * vb / sms / 1e6, read / sms / 1e6))
+        print("%-36s ok=%s bits/val=%5.2f exc/vec=%6.1f bw=%s | decode %.3f ms %6.0f GB/s out, %6.0f GB/s algo (%.3f of peak) | encode %.3f ms %6.0f GB/s in, %6.0f algo (%.3f); unordered %.3f ms (%.3f) | sum-scan %.3f ms %6.0f GB/s decoded-equivalent %5.0f GB/s read (%.3f)" % (
+            name, ok, 8.0 * read / n, ne / col.n_vectors, sorted(set(meta["bw"].tolist()))[:4], ms, n * vb / ms / 1e6, algo / ms / 1e6, algo / ms / 1e6 / PEAK,
+            ems, n * vb / ems / 1e6, algo / ems / 1e6, algo / ems / 1e6 / PEAK, ums, algo / ums / 1e6 / PEAK, sms, n * vb / sms / 1e6, read / sms / 1e6, read / sms / 1e6 / PEAK))
         del col, out
 
 

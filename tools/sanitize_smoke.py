@@ -20,14 +20,18 @@ cols = [
     torch.from_numpy(rng.integers(0, 1 << 32, size=1024 * 9, dtype=np.uint64).astype(np.uint32).view(np.float32)).to(dev),
     torch.zeros(4096, dtype=torch.float32, device=dev),
 ]
+# integers of every FFOR width (one vector each): the in-place packers, the wide direct path, the SUM fast / slow paths
+cols.append(torch.from_numpy(np.concatenate([rng.integers(0, 1 << w, size=1024, dtype=np.uint64).astype(np.float64) for w in range(0, 53)])).to(dev))
+cols.append(torch.from_numpy(np.concatenate([rng.integers(0, 1 << w, size=1024, dtype=np.uint64).astype(np.float32) for w in range(0, 24)])).to(dev))
 for x in cols:
-    col = alp_b200.encode(x)
-    col.read_totals()
-    y = alp_b200.decode(col)
-    ib = torch.int64 if x.element_size() == 8 else torch.int32
-    assert torch.equal(x.view(ib), y.view(ib))
-    s = alp_b200.decode_sum(col)
-    torch.cuda.synchronize()
+    for ordered in (True, False):
+        col = alp_b200.encode(x, ordered=ordered)
+        col.read_totals()
+        y = alp_b200.decode(col)
+        ib = torch.int64 if x.element_size() == 8 else torch.int32
+        assert torch.equal(x.view(ib), y.view(ib))
+        s = alp_b200.decode_sum(col)
+        torch.cuda.synchronize()
 from alp_b200 import primitives as gpu  # noqa: E402
 
 v = (rng.integers(0, 100000, 1024) / 100.0)
@@ -40,5 +44,6 @@ assert d.tobytes() == v.tobytes()
 codec = alp_b200.HostCodec(300, 8)
 h = codec.compress(np.ascontiguousarray(cols[0].cpu().numpy()[:200000]))
 assert codec.decompress(h).tobytes() == cols[0].cpu().numpy()[:200000].tobytes()
+codec.sum(h)
 codec.close()
 print("sanitize smoke OK")
