@@ -55,7 +55,7 @@ int device_info(DeviceInfo& out) {
 }
 
 size_t encode_workspace_bytes(uint64_t n_vectors) {
-	const uint64_t blocks = (n_vectors + ENC_WARPS - 1) / ENC_WARPS;
+	const uint64_t blocks = (n_vectors + ENC_MIN_WARPS - 1) / ENC_MIN_WARPS;
 	return (size_t)((2 + 2 * blocks) * sizeof(uint64_t) + 255) & ~(size_t)255;
 }
 
@@ -64,6 +64,8 @@ size_t encode_workspace_bytes(uint64_t n_vectors) {
 // =====================================================================================================================
 // Host-buffer codec context
 // =====================================================================================================================
+constexpr int MAX_CHUNKS = 16;  // pipeline depth of compress_host
+
 struct alpb200_ctx {
 	int          device      = 0;
 	int          value_bytes = 8;
@@ -81,7 +83,9 @@ struct alpb200_ctx {
 	void*             d_ws_enc  = nullptr;
 	void*             d_ws_init = nullptr;
 	uint64_t          packed_capacity = 0, exc_capacity = 0;
-	uint64_t*         h_totals = nullptr;  // pinned
+	uint64_t*         h_totals = nullptr;  // pinned: one 4-word snapshot of the column totals per compress chunk
+	cudaEvent_t       chunk_in[MAX_CHUNKS]  = {};
+	cudaEvent_t       chunk_enc[MAX_CHUNKS] = {};
 	bool              unordered = false;   // ALPB200_OPT_UNORDERED: compress_host encodes with the completion-order layout
 };
 
@@ -93,6 +97,10 @@ void ctx_release(alpb200_ctx* c) {
 	for (int i = 0; i < 3; i++) {
 		if (c->streams[i]) { cudaStreamDestroy(c->streams[i]); }
 		if (c->events[i]) { cudaEventDestroy(c->events[i]); }
+	}
+	for (int i = 0; i < MAX_CHUNKS; i++) {
+		if (c->chunk_in[i]) { cudaEventDestroy(c->chunk_in[i]); }
+		if (c->chunk_enc[i]) { cudaEventDestroy(c->chunk_enc[i]); }
 	}
 	cudaFree(c->d_values);
 	cudaFree(c->d_meta);
@@ -107,6 +115,11 @@ void ctx_release(alpb200_ctx* c) {
 	delete c;
 }
 
+// Chunked pipeline over three streams: while chunk i is analysed and encoded, chunk i+1's values are already on their
+// way to the device and chunk i-1's compressed bytes on their way back (PCIe is full duplex).  Chunks are whole
+// row-groups; each chunk's encode APPENDS to the column (the kernel continues at the running totals, which never leave
+// the device), so the result is the same column a single launch would produce.  The host learns a chunk's byte range
+// from a 32-byte snapshot of the totals and drains it one chunk behind the launches.
 template <typename PT>
 int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_column* h_col) {
 	if (!c || !h_in || !h_col || !h_col->meta || !h_col->packed || !h_col->exc_val || !h_col->exc_pos || !h_col->totals) {
@@ -117,45 +130,78 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_
 	const uint64_t n_values = n_vec * VEC;  // padded length
 	if (n_vec > c->max_vectors || n_vec > h_col->n_vectors) { return fail(ALPB200_EINVAL, "compress_host: column larger than the context / container"); }
 	CUDA_TRY(cudaSetDevice(c->device));
-	cudaStream_t s = c->streams[0];
 	if (n_vec == 0) {
 		h_col->n_vectors = 0;
 		h_col->n_values  = 0;
 		std::memset(h_col->totals, 0, 4 * sizeof(uint64_t));
 		return ALPB200_OK;
 	}
-	CUDA_TRY(cudaMemcpyAsync(c->d_values, h_in, n_values_in * sizeof(PT), cudaMemcpyHostToDevice, s));
-	if (n_values != n_values_in) {
-		TRY(launch_pad_tail<PT>(static_cast<PT*>(c->d_values), n_values_in, n_values, s));
+	cudaStream_t   s_in = c->streams[0], s_enc = c->streams[1], s_out = c->streams[2];
+	const uint64_t n_rg      = (n_vec + ALPB200_ROWGROUP_VECTORS - 1) / ALPB200_ROWGROUP_VECTORS;
+	const uint64_t chunk_rg  = std::max<uint64_t>(10, (n_rg + MAX_CHUNKS - 1) / MAX_CHUNKS);  // at least ~8 MiB of f64 per chunk
+	const uint64_t chunk_vec = chunk_rg * ALPB200_ROWGROUP_VECTORS;
+	const int      n_chunks  = (int)((n_vec + chunk_vec - 1) / chunk_vec);
+	PT*            d_values  = static_cast<PT*>(c->d_values);
+	uint64_t       prev_p = 0, prev_e = 0;
+	int            rc = ALPB200_OK;
+
+	// copy chunk k's part of the column back (called one chunk behind the launches, and once more at the end)
+	auto drain = [&](int k) -> int {
+		CUDA_TRY(cudaEventSynchronize(c->chunk_enc[k]));
+		const uint64_t* tot = c->h_totals + 4 * k;
+		if (tot[2] != 0) { return fail(ALPB200_ECAPACITY, "compress_host: device staging capacity exceeded"); }
+		const uint64_t p1 = tot[0], e1 = tot[1];
+		if (p1 > h_col->packed_capacity || e1 > h_col->exc_capacity) { return fail(ALPB200_ECAPACITY, "compress_host: the host column container is too small"); }
+		const uint64_t v0 = (uint64_t)k * chunk_vec, v1 = std::min(n_vec, v0 + chunk_vec);
+		CUDA_TRY(cudaMemcpyAsync(h_col->meta + v0, c->d_meta + v0, (v1 - v0) * sizeof(alpb200_vec_meta), cudaMemcpyDeviceToHost, s_out));
+		if (p1 > prev_p) { CUDA_TRY(cudaMemcpyAsync(h_col->packed + prev_p, c->d_packed + prev_p, p1 - prev_p, cudaMemcpyDeviceToHost, s_out)); }
+		if (e1 > prev_e) {
+			CUDA_TRY(cudaMemcpyAsync(static_cast<PT*>(h_col->exc_val) + prev_e, static_cast<PT*>(c->d_exc_val) + prev_e, (e1 - prev_e) * sizeof(PT),
+			                         cudaMemcpyDeviceToHost, s_out));
+			CUDA_TRY(cudaMemcpyAsync(h_col->exc_pos + prev_e, c->d_exc_pos + prev_e, (e1 - prev_e) * sizeof(uint16_t), cudaMemcpyDeviceToHost, s_out));
+		}
+		prev_p = p1;
+		prev_e = e1;
+		return ALPB200_OK;
+	};
+	auto launch_chunk = [&](int k) -> int {
+		const uint64_t v0 = (uint64_t)k * chunk_vec, v1 = std::min(n_vec, v0 + chunk_vec);
+		const uint64_t x0 = v0 * VEC, x1 = std::min(n_values_in, v1 * VEC);
+		CUDA_TRY(cudaMemcpyAsync(d_values + x0, h_in + x0, (x1 - x0) * sizeof(PT), cudaMemcpyHostToDevice, s_in));
+		if (v1 == n_vec && n_values != n_values_in) { TRY(launch_pad_tail<PT>(d_values, n_values_in, n_values, s_in)); }
+		CUDA_TRY(cudaEventRecord(c->chunk_in[k], s_in));
+		CUDA_TRY(cudaStreamWaitEvent(s_enc, c->chunk_in[k], 0));
+		alpb200_rg_state* states = c->d_states + v0 / ALPB200_ROWGROUP_VECTORS;
+		TRY(launch_init<PT>(d_values + x0, (v1 - v0) * VEC, states, c->d_ws_init, s_enc));
+		alpb200_column d_col {};
+		d_col.n_vectors       = v1 - v0;
+		d_col.meta            = c->d_meta + v0;
+		d_col.packed          = c->d_packed;
+		d_col.packed_capacity = c->packed_capacity;
+		d_col.exc_val         = c->d_exc_val;
+		d_col.exc_pos         = c->d_exc_pos;
+		d_col.exc_capacity    = c->exc_capacity;
+		d_col.totals          = c->d_totals;
+		TRY(launch_encode<PT>(d_values + x0, v1 - v0, states, &d_col, c->d_ws_enc, s_enc, !c->unordered, /*append=*/k > 0));
+		CUDA_TRY(cudaMemcpyAsync(c->h_totals + 4 * k, c->d_totals, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_enc));
+		CUDA_TRY(cudaEventRecord(c->chunk_enc[k], s_enc));
+		return ALPB200_OK;
+	};
+	for (int k = 0; k < n_chunks && rc == ALPB200_OK; k++) {
+		rc = launch_chunk(k);
+		if (rc == ALPB200_OK && k > 0) { rc = drain(k - 1); }
 	}
-	TRY(launch_init<PT>(static_cast<const PT*>(c->d_values), n_values, c->d_states, c->d_ws_init, s));
-	alpb200_column d_col {};
-	d_col.n_vectors       = n_vec;
-	d_col.meta            = c->d_meta;
-	d_col.packed          = c->d_packed;
-	d_col.packed_capacity = c->packed_capacity;
-	d_col.exc_val         = c->d_exc_val;
-	d_col.exc_pos         = c->d_exc_pos;
-	d_col.exc_capacity    = c->exc_capacity;
-	d_col.totals          = c->d_totals;
-	TRY(launch_encode<PT>(static_cast<const PT*>(c->d_values), n_vec, c->d_states, &d_col, c->d_ws_enc, s, !c->unordered));
-	CUDA_TRY(cudaMemcpyAsync(c->h_totals, c->d_totals, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-	CUDA_TRY(cudaMemcpyAsync(h_col->meta, c->d_meta, n_vec * sizeof(alpb200_vec_meta), cudaMemcpyDeviceToHost, s));
-	CUDA_TRY(cudaStreamSynchronize(s));
-	const uint64_t packed_bytes = c->h_totals[0], n_exc = c->h_totals[1];
-	if (c->h_totals[2] != 0) { return fail(ALPB200_ECAPACITY, "compress_host: device staging capacity exceeded"); }
-	if (packed_bytes > h_col->packed_capacity || n_exc > h_col->exc_capacity) {
-		return fail(ALPB200_ECAPACITY, "compress_host: the host column container is too small");
+	if (rc == ALPB200_OK) { rc = drain(n_chunks - 1); }
+	for (int i = 0; i < 3; i++) {  // also on failure: nothing may still be running on the caller's buffers
+		cudaError_t err = cudaStreamSynchronize(c->streams[i]);
+		if (err != cudaSuccess && rc == ALPB200_OK) { rc = fail(ALPB200_ECUDA, "compress_host: %s", cudaGetErrorString(err)); }
 	}
-	CUDA_TRY(cudaMemcpyAsync(h_col->packed, c->d_packed, packed_bytes, cudaMemcpyDeviceToHost, s));
-	CUDA_TRY(cudaMemcpyAsync(h_col->exc_val, c->d_exc_val, n_exc * sizeof(PT), cudaMemcpyDeviceToHost, c->streams[1]));
-	CUDA_TRY(cudaMemcpyAsync(h_col->exc_pos, c->d_exc_pos, n_exc * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->streams[1]));
-	CUDA_TRY(cudaStreamSynchronize(s));
-	CUDA_TRY(cudaStreamSynchronize(c->streams[1]));
+	if (rc != ALPB200_OK) { return rc; }
+	const uint64_t* tot    = c->h_totals + 4 * (n_chunks - 1);
 	h_col->n_vectors       = n_vec;
 	h_col->n_values        = n_values_in;
-	h_col->max_block_bytes = c->h_totals[3];
-	std::memcpy(h_col->totals, c->h_totals, 4 * sizeof(uint64_t));
+	h_col->max_block_bytes = tot[3];
+	std::memcpy(h_col->totals, tot, 4 * sizeof(uint64_t));
 	return ALPB200_OK;
 }
 
@@ -406,7 +452,11 @@ int alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int 
 	alloc(reinterpret_cast<void**>(&c->d_states), n_rg * sizeof(alpb200_rg_state));
 	alloc(&c->d_ws_enc, encode_workspace_bytes(max_vectors));
 	alloc(&c->d_ws_init, init_workspace_bytes(max_vectors * VEC));
-	if (err == cudaSuccess) { err = cudaHostAlloc(reinterpret_cast<void**>(&c->h_totals), 4 * sizeof(uint64_t), cudaHostAllocDefault); }
+	if (err == cudaSuccess) { err = cudaHostAlloc(reinterpret_cast<void**>(&c->h_totals), MAX_CHUNKS * 4 * sizeof(uint64_t), cudaHostAllocDefault); }
+	for (int i = 0; i < MAX_CHUNKS && err == cudaSuccess; i++) {
+		err = cudaEventCreateWithFlags(&c->chunk_in[i], cudaEventDisableTiming);
+		if (err == cudaSuccess) { err = cudaEventCreateWithFlags(&c->chunk_enc[i], cudaEventDisableTiming); }
+	}
 	for (int i = 0; i < 3 && err == cudaSuccess; i++) {
 		err = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
 		if (err == cudaSuccess) { err = cudaEventCreateWithFlags(&c->events[i], cudaEventDisableTiming); }

@@ -623,8 +623,8 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
 // run by one warp: aggregates[0..n_blocks) -> prefixes[0..n_blocks) (exclusive), in order.  Each step looks at the
 // next 128 aggregates and publishes prefixes for the leading run that is already valid, so a block never waits for
 // blocks behind it.
-__device__ __forceinline__ void scan_blocks(const uint64_t* aggregates, uint64_t* prefixes, uint32_t n_blocks, int t) {
-	uint64_t running = 0;
+__device__ __forceinline__ void scan_blocks(const uint64_t* aggregates, uint64_t* prefixes, uint32_t n_blocks, int t, uint64_t start) {
+	uint64_t running = start;
 	uint32_t base    = 0;
 	while (base < n_blocks) {
 		uint64_t v[4];
@@ -680,8 +680,9 @@ struct ColOut {
 	uint64_t*         totals;
 };
 
-// workspace layout: [0] ticket counter, [1] reserved, [2 .. 2+n_blocks) block aggregates, [2+n_blocks .. 2+2*n_blocks)
-// exclusive prefixes.
+// workspace layout: [0] ticket counter, [1] where this call's output starts (packed units << 32 | exception slots: 0, or
+// the column's running totals when appending — set by encode_prepare_kernel; completion order allocates from it with
+// atomics), [2 .. 2+n_blocks) block aggregates, [2+n_blocks .. 2+2*n_blocks) exclusive prefixes.
 //
 // One CTA = WARPS vectors, one warp each.  Per warp:
 //   1  the vector arrives in a per-warp shared-memory tile with one bulk-async copy (TMA 1-D)
@@ -713,15 +714,24 @@ struct EncodeCfg<double> {
 	static constexpr bool     TWO_PASS      = false;
 	static constexpr uint32_t SMEM_PER_WARP = VEC * sizeof(double);  // the tile
 	static constexpr uint32_t INPLACE_MAX   = 32;                    // widest block packed in place
-	static constexpr int      WARPS_PER_SM  = 24;  // 8 KiB of shared memory and 80 registers per thread
+	// 9 warps x 3 blocks = 27 warps per SM: what 227 KiB of shared memory hold at 8 KiB a vector (72 registers per thread).
+	// Measured against 8 x 3 (80 registers): 2-3 % faster.
+	static constexpr int      WARPS         = 9;
+	static constexpr int      WARPS_PER_SM  = 27;
 };
 template <>
 struct EncodeCfg<float> {
 	static constexpr bool     TWO_PASS      = ALPB200_ENC_F32_TWO_PASS != 0;
 	static constexpr uint32_t SMEM_PER_WARP = 35 * 128u;  // tile (32 units); every f32 block fits: 32 bits, or ALP_RD 31 + 3
 	static constexpr uint32_t INPLACE_MAX   = 32;
+	static constexpr int      WARPS         = 8;
 	static constexpr int      WARPS_PER_SM  = 32;  // 4.4 KiB and 64 registers
 };
+
+// runs after the workspace was zeroed: appending calls continue at the column's running totals
+static __global__ void encode_prepare_kernel(uint64_t* workspace, const uint64_t* totals, int append) {
+	workspace[1] = append ? (((totals[0] / 128ull) << 32) | (totals[1] & 0xFFFFFFFFull)) : 0ull;
+}
 
 template <typename PT, int WARPS, bool ORDERED>
 __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARPS) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
@@ -737,9 +747,14 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	__shared__ __align__(8) uint64_t s_bar[WARPS];
 
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
-	if (threadIdx.x == 0) { s_bid = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace), 1ull); }
-	__syncthreads();
-	const uint32_t bid    = s_bid;
+	// ORDERED: tickets are drawn when a block starts, so every predecessor of a waiting block is resident (no deadlock)
+	// and ticket order = start order.  Completion order needs neither: the block index will do, one L2 round trip saved.
+	uint32_t bid = blockIdx.x;
+	if constexpr (ORDERED) {
+		if (threadIdx.x == 0) { s_bid = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace), 1ull); }
+		__syncthreads();
+		bid = s_bid;
+	}
 	const uint64_t v      = (uint64_t)bid * WARPS + warp;
 	const bool     active = v < n_vectors;
 	uint8_t*       mine   = smem + (size_t)warp * Cfg::SMEM_PER_WARP;  // the tile (two-pass f32: the packed-block stage)
@@ -792,7 +807,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	__syncthreads();
 	uint64_t* aggregates = workspace + 2;
 	uint64_t* prefixes   = aggregates + gridDim.x;
-	uint64_t  agg        = 0;
+	uint64_t  agg        = 0, early_excl = 0;
 	if (warp == 0) {
 		uint64_t mine_agg = 0;
 		if (t < WARPS) { mine_agg = ((uint64_t)s_units[t] << 32) | s_cnt[t]; }
@@ -806,7 +821,15 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		}
 		if (t < WARPS) { s_pre[t] = incl - mine_agg; }
 		if (t == 0) {
-			if constexpr (ORDERED) { st_volatile_u64(&aggregates[bid], SCAN_VALID | agg); }
+			if constexpr (ORDERED) {
+				st_volatile_u64(&aggregates[bid], SCAN_VALID | agg);
+			} else {
+				// completion order: one atomic hands out the block's space (its round trip overlaps the packing below);
+				// the running totals are the column totals
+				early_excl = (uint64_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace + 1), (unsigned long long)agg);
+				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[0]), (unsigned long long)(agg >> 32) * 128ull);
+				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & 0xFFFFFFFFull));
+			}
 			atomicMax(reinterpret_cast<unsigned long long*>(&col.totals[3]), (unsigned long long)wide * 128ull);
 		}
 	}
@@ -834,13 +857,10 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	if (warp == 0) {
 		uint64_t excl = 0;
 		if constexpr (!ORDERED) {
-			// completion order: one atomic hands out the block's space; the running totals are the column totals
-			if (t == 0) {
-				excl = (uint64_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace + 1), (unsigned long long)agg);
-				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[0]), (unsigned long long)(agg >> 32) * 128ull);
-				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & 0xFFFFFFFFull));
-			}
-		} else if (bid != 0) {
+			excl = early_excl;
+		} else if (bid == 0) {
+			if (t == 0) { excl = workspace[1]; }  // where this call's output starts (0 unless appending)
+		} else {
 			// (Blocks resolving their own prefix from a window of predecessors next to the scanner — one L2 round trip
 			// instead of three — was measured twice and lost both times: 128-wide without back-off, ~1 TB/s of polling on
 			// L2, 4.65 vs 3.9 ms; 32-wide with back-off and all 32 lanes of this warp polling, 1.66 vs 1.52 ms per 2^29.)
@@ -861,14 +881,14 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	__syncthreads();
 	const bool scanner = ORDERED && bid == 0 && warp == WARPS - 1;  // this warp produces every block's prefix once its own work is done
 	if (!active) {
-		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t); }
+		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t, workspace[1]); }
 		return;
 	}
 	const uint64_t my_excl   = s_excl + s_pre[warp];  // both halves add without carry into each other (sizes checked below)
 	const uint64_t units_off = my_excl >> 32, exc_off = my_excl & 0xFFFFFFFFull;
 	if (units_off * 128ull + bytes > col.packed_capacity || exc_off + a.cnt > col.exc_capacity) {
 		if (t == 0) { atomicExch(reinterpret_cast<unsigned long long*>(&col.totals[2]), 1ull); }
-		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t); }
+		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t, workspace[1]); }
 		return;
 	}
 	uint8_t* dst = col.packed + units_off * 128ull;
@@ -916,7 +936,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	}
 	if (scanner) {
 		__syncwarp();
-		scan_blocks(aggregates, prefixes, gridDim.x, t);
+		scan_blocks(aggregates, prefixes, gridDim.x, t, workspace[1]);
 	}
 }
 

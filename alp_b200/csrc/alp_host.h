@@ -26,10 +26,7 @@ int fail(int code, const char* fmt, const char* a = "", const char* b = "");
 	} while (0)
 
 constexpr int DEC_WARPS = 8;
-#ifndef ALPB200_ENC_WARPS
-#define ALPB200_ENC_WARPS 8  // vectors (warps) per encode thread block
-#endif
-constexpr int ENC_WARPS = ALPB200_ENC_WARPS;
+constexpr int ENC_MIN_WARPS = 8;  // fewest vectors per encode thread block (EncodeCfg<PT>::WARPS); sizes the workspace
 
 struct DeviceInfo {
 	int sms        = 0;
@@ -47,12 +44,16 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 template <typename PT>
 int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream);
 template <typename PT, bool ORDERED>
-int launch_encode_impl(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream);
-// ordered = true: blocks in vector order (alpb200_encode_*); false: completion order (alpb200_encode_unordered_*)
+int launch_encode_impl(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
+                       bool append);
+// ordered = true: blocks in vector order (alpb200_encode_*); false: completion order (alpb200_encode_unordered_*).
+// append  = true: the output continues where col->totals says the column ends (meta / d_in / d_states point at the
+//                 first vector of this call; packed / exc arrays and their offsets stay those of the whole column).
 template <typename PT>
 inline int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
-                         bool ordered = true) {
-	return ordered ? launch_encode_impl<PT, true>(d_in, n, d_states, col, ws, stream) : launch_encode_impl<PT, false>(d_in, n, d_states, col, ws, stream);
+                         bool ordered = true, bool append = false) {
+	return ordered ? launch_encode_impl<PT, true>(d_in, n, d_states, col, ws, stream, append)
+	               : launch_encode_impl<PT, false>(d_in, n, d_states, col, ws, stream, append);
 }
 template <typename PT>
 int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream);

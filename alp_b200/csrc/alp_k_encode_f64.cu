@@ -2,5 +2,5 @@
 #include "alp_k_encode.inc"
 
 namespace alpb200 {
-template int launch_encode_impl<double, true>(const double*, uint64_t, const alpb200_rg_state*, const alpb200_column*, void*, void*);
+template int launch_encode_impl<double, true>(const double*, uint64_t, const alpb200_rg_state*, const alpb200_column*, void*, void*, bool);
 }

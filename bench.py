@@ -323,7 +323,7 @@ def main():
     scan_ms = s0.elapsed_time(s1) / args.steps
 
     # ---- e2e: host column in, host values out, through alpb200_decompress_host ----
-    e2e = e2e_scan = None
+    e2e = e2e_scan = e2e_compress = None
     if not args.no_e2e:
         hcol = pinned_host_column(col.to_host())
         hout_t = torch.empty(n, dtype=torch.float64, pin_memory=True)
@@ -370,6 +370,29 @@ def main():
             "d2h_bytes_per_step": 8,
             "ms_per_step": scan_s * 1e3,
             "api": "alpb200_sum_host_f64 (SUM over the host column; reference: bench_end_to_end alp_func + aggr_plus)",
+        }
+        # the other direction end to end: pinned host values in, pinned host column out (chunk pipeline, H2D-bound)
+        ref_packed = hcol.packed[: hcol.packed_bytes].tobytes()
+        hcol.packed[: hcol.packed_bytes] = 0
+        codec.compress(hout, col=hcol)  # warm-up + check: the same column comes back
+        assert hcol.packed[: hcol.packed_bytes].tobytes() == ref_packed
+        del ref_packed
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            codec.compress(hout, col=hcol)
+        comp_s = (time.perf_counter() - t0) / args.e2e_steps
+        tc = torch.tensor([comp_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        comp_s = float(tc.item())
+        e2e_compress = {
+            "value": world * n * 8.0 / comp_s / 1e9,
+            "unit": "GB/s of f64 input compressed",
+            "h2d_bytes_per_step": int(n * 8),
+            "d2h_bytes_per_step": int(h2d),
+            "ms_per_step": comp_s * 1e3,
+            "api": "alpb200_compress_host_f64 (pinned host buffers; row-group init + encode per chunk, 16-chunk pipeline over 3 streams)",
         }
         codec.close()
 
@@ -438,6 +461,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "e2e_scan": e2e_scan,
+            "e2e_compress": e2e_compress,
             "encode": {
                 "GBps": enc_gbps,
                 "ms": encode_ms,

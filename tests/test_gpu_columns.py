@@ -395,6 +395,24 @@ def test_host_codec_round_trip(kind, checker):
     codec.close()
 
 
+@pytest.mark.parametrize("kind,n_vec", [(2, 16 * 1000 + 3 * 100 + 41), (3, 2300), (4, 40 * 100)])
+def test_pipelined_host_compress_equals_one_launch(kind, n_vec):
+    """alpb200_compress_host pipelines the column in chunks of whole row-groups whose encodes APPEND to the column; the
+    result must be byte for byte the column one device launch produces (several chunks, a ragged last row-group)."""
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    x = pyoracle.generate(n_vec * 1024, kind)
+    codec = alp_b200.HostCodec(n_vec, x.dtype.itemsize)
+    got = codec.compress(x)
+    codec.close()
+    want = alp_b200.encode(torch.from_numpy(x).to(_dev())).to_host()
+    _assert_columns_equal(got, want, "pipelined-compress")
+    assert int(got.totals[3]) == int(want.totals[3])
+
+
 def test_large_column_properties():
     """2^26 values (BASELINE config 2 at 1/16 scale; the full size runs in bench.py, which verifies its round trip
     too): encode→decode is the identity, sizes match the per-vector metadata, positions are sorted, blocks are dense."""
