@@ -39,6 +39,8 @@ SIGNATURES = {
     "alpb200_encode_workspace_bytes": ([_c.c_uint64], _c.c_size_t),
     "alpb200_encode_f64": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
     "alpb200_encode_f32": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
+    "alpb200_encode_ex_f64": ([_P, _c.c_uint64, _P, _P, _P, _P, _c.c_uint32], _c.c_int),
+    "alpb200_encode_ex_f32": ([_P, _c.c_uint64, _P, _P, _P, _P, _c.c_uint32], _c.c_int),
     "alpb200_encode_unordered_f64": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
     "alpb200_encode_unordered_f32": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
     "alpb200_decode_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),

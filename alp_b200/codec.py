@@ -140,9 +140,11 @@ def rowgroup_init(values):
     return states
 
 
-def encode(values, states=None, col=None, workspace=None, ordered=True):
+def encode(values, states=None, col=None, workspace=None, ordered=True, append_at=None):
     """Compress a device column (numel a multiple of 1024) → DeviceColumn.  `states` defaults to rowgroup_init(values).
-    ordered=False selects the completion-order layout (alpb200_encode_unordered_*): same blocks, faster, bytes not reproducible."""
+    ordered=False selects the completion-order layout (alpb200_encode_unordered_*): same blocks, faster, bytes not reproducible.
+    append_at=v (a multiple of 100, with `col` given): `values` are the vectors v, v+1, ... of `col`, whose earlier vectors
+    were encoded by previous calls; the output continues where the column ends (ALPB200_ENCODE_APPEND)."""
     _require_cuda(values, "values")
     vb = values.element_size()
     if values.dtype != _FLOAT[vb] or values.numel() % _abi.VECTOR_SIZE:
@@ -152,13 +154,22 @@ def encode(values, states=None, col=None, workspace=None, ordered=True):
         states = rowgroup_init(values)
     _require_cuda(states, "states")
     if col is None:
+        if append_at is not None:
+            raise ValueError("append_at needs the column that is being continued")
         col = DeviceColumn(n_vec, vb, values.device)
     if workspace is None:
         workspace = torch.empty(max(256, lib.alpb200_encode_workspace_bytes(n_vec)), dtype=torch.uint8, device=values.device)
     st = col.as_struct()
+    flags = 0 if ordered else 1
+    if append_at is not None:
+        if append_at % _abi.ROWGROUP_VECTORS or append_at + n_vec > col.n_vectors:
+            raise ValueError("append_at must start a row-group inside the column")
+        st.meta = col.meta.data_ptr() + append_at * 32
+        st.n_vectors = n_vec
+        flags |= 2 if append_at > 0 else 0
     with torch.cuda.device(values.device):
-        fn = getattr(lib, ("alpb200_encode_" if ordered else "alpb200_encode_unordered_") + _sfx(vb))
-        check(fn(values.data_ptr(), n_vec, states.data_ptr(), ctypes.byref(st), workspace.data_ptr(), _stream_ptr(values.device)))
+        fn = getattr(lib, "alpb200_encode_ex_" + _sfx(vb))
+        check(fn(values.data_ptr(), n_vec, states.data_ptr(), ctypes.byref(st), workspace.data_ptr(), _stream_ptr(values.device), flags))
     return col
 
 

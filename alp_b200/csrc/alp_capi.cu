@@ -406,6 +406,17 @@ int alpb200_encode_unordered_f32(const float* d_in, uint64_t n_vectors, const al
 	return launch_encode<float>(d_in, n_vectors, d_states, col, ws, stream, false);
 }
 
+int alpb200_encode_ex_f64(const double* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws,
+                          void* stream, uint32_t flags) {
+	if (flags & ~(ALPB200_ENCODE_UNORDERED | ALPB200_ENCODE_APPEND)) { return fail(ALPB200_EINVAL, "encode_ex: unknown flag"); }
+	return launch_encode<double>(d_in, n_vectors, d_states, col, ws, stream, !(flags & ALPB200_ENCODE_UNORDERED), (flags & ALPB200_ENCODE_APPEND) != 0);
+}
+int alpb200_encode_ex_f32(const float* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws,
+                          void* stream, uint32_t flags) {
+	if (flags & ~(ALPB200_ENCODE_UNORDERED | ALPB200_ENCODE_APPEND)) { return fail(ALPB200_EINVAL, "encode_ex: unknown flag"); }
+	return launch_encode<float>(d_in, n_vectors, d_states, col, ws, stream, !(flags & ALPB200_ENCODE_UNORDERED), (flags & ALPB200_ENCODE_APPEND) != 0);
+}
+
 int alpb200_decode_f64(const alpb200_column* col, uint64_t first, uint64_t n, double* d_out, void* stream) {
 	// d_out receives vector `first + i` at d_out[i * 1024]
 	return launch_decode<double>(col, first, n, d_out, stream);

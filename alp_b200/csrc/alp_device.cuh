@@ -194,23 +194,31 @@ __device__ __forceinline__ int64_t shfl_xor_i64(int64_t v, int m) {
 }
 __device__ __forceinline__ int32_t shfl_xor_i64(int32_t v, int m) { return __shfl_xor_sync(FULL, v, m); }
 
+// warp-wide signed min / max on the hardware reduction (REDUX): 32-bit directly; 64-bit as high word first, then the low
+// words of the lanes that hold the winning high word (4 instructions instead of 5 shuffle + compare/select rounds)
+__device__ __forceinline__ int32_t warp_min_impl(int32_t v) { return __reduce_min_sync(FULL, v); }
+__device__ __forceinline__ int32_t warp_max_impl(int32_t v) { return __reduce_max_sync(FULL, v); }
+__device__ __forceinline__ int64_t warp_min_impl(int64_t v) {
+	const int32_t  hi  = (int32_t)(v >> 32);
+	const uint32_t lo  = (uint32_t)v;
+	const int32_t  mhi = __reduce_min_sync(FULL, hi);
+	const uint32_t mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xFFFFFFFFu);
+	return (int64_t)(((uint64_t)(uint32_t)mhi << 32) | mlo);
+}
+__device__ __forceinline__ int64_t warp_max_impl(int64_t v) {
+	const int32_t  hi  = (int32_t)(v >> 32);
+	const uint32_t lo  = (uint32_t)v;
+	const int32_t  mhi = __reduce_max_sync(FULL, hi);
+	const uint32_t mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+	return (int64_t)(((uint64_t)(uint32_t)mhi << 32) | mlo);
+}
 template <typename ST>
 __device__ __forceinline__ ST warp_min(ST v) {
-#pragma unroll
-	for (int m = 16; m > 0; m >>= 1) {
-		ST o = shfl_xor_i64(v, m);
-		v    = o < v ? o : v;
-	}
-	return v;
+	return warp_min_impl(v);
 }
 template <typename ST>
 __device__ __forceinline__ ST warp_max(ST v) {
-#pragma unroll
-	for (int m = 16; m > 0; m >>= 1) {
-		ST o = shfl_xor_i64(v, m);
-		v    = o > v ? o : v;
-	}
-	return v;
+	return warp_max_impl(v);
 }
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
 	uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src);

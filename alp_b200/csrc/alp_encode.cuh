@@ -146,6 +146,8 @@ struct GlobalIO {
 	}
 	template <int R>
 	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT) {}
+	// value i of the vector (second-level sampling)
+	__device__ __forceinline__ PT sample(const PT* in_vec, int i) const { return in_vec[i]; }
 	// start over (the analysis is redone with the exact per-value recipe)
 	__device__ __forceinline__ void rewind(const PT* in_vec) {
 #pragma unroll
@@ -169,6 +171,8 @@ struct TileIO {
 	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT v) {
 		tile[Map<PT>::index(t, R)] = v;
 	}
+	// value i of the vector (second-level sampling; before the analysis overwrites the tile): no trip to global memory
+	__device__ __forceinline__ PT sample(const PT*, int i) const { return Traits<PT>::from_bits(tile[i]); }
 	// start over: the tile was overwritten with encoded integers; every thread restores ITS OWN slots from global memory
 	__device__ __forceinline__ void rewind(const PT* in_vec) {
 #pragma unroll 8
@@ -299,7 +303,7 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 	using UT = typename T::UT;
 	using ST = typename T::ST;
 	int e = st.exp_of(0), f = st.fac_of(0);
-	if (st.k > 1) { choose_exponent_factor<PT>(in_vec[32 * t], st, e, f); }  // encoder.hpp:409-412
+	if (st.k > 1) { choose_exponent_factor<PT>(io.sample(in_vec, 32 * t), st, e, f); }  // encoder.hpp:409-412
 
 	RowAcc<PT> acc;
 	if (!analyze_rows<PT, true>(io, e, f, acc)) {
@@ -545,48 +549,88 @@ __device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_
 }
 
 // ---- exception emission in position order (encoder.hpp:390-397 / rd.hpp:138-142) ------------------------------------
-// value_of(p) returns what is stored for position p (the original value for ALP, the left part for ALP_RD).
-template <typename PT, typename ValueOf, typename Store>
-__device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&& value_of, Store&& store) {
-	if (!__any_sync(FULL, myexc != 0)) { return; }
-	const uint32_t rowmask = transpose32(myexc, t);  // lane r: ballot of "is exception" over row r
-	// Lane r now knows how many exceptions precede row r; every thread then walks ITS OWN exceptions and fetches the
-	// prefix of each one's row from lane r.  The loop runs max-exceptions-per-thread times (2-4 for a typical vector)
-	// instead of once per row that holds an exception.
-	uint32_t m = myexc;
+// Split in two so that the batched encoder can do everything that does not need the output offset BEFORE it waits for
+// it: plan_exceptions (ranks: a 32x32 bit-matrix transpose of the per-thread bitmaps and two warp scans) and
+// preload_exceptions (the first K values of every thread, fetched with independent loads instead of one L2 round trip
+// per loop iteration).  emit_planned then only shuffles and stores.
+//   value_of(p) returns what is stored for position p (the original value for ALP, the left part for ALP_RD).
+struct ExcPlan {
+	uint32_t rowmask;  // lane r: ballot of "is exception" over the threads' row r
+	uint32_t pre;      // lane r: exceptions before row r (64-bit lanes: low / high 16 bits for the two halves of the warp)
+	bool     any;
+};
+template <typename PT>
+__device__ __forceinline__ ExcPlan plan_exceptions(uint32_t myexc, int t) {
+	ExcPlan pl;
+	pl.any     = __any_sync(FULL, myexc != 0);
+	pl.rowmask = 0;
+	pl.pre     = 0;
+	if (!pl.any) { return pl; }
+	pl.rowmask = transpose32(myexc, t);
 	if (sizeof(PT) == 8) {
-		const int lane = t & 15, half = t >> 4;
-		uint32_t  tot_lo, tot_hi;
-		const uint32_t p_lo = warp_excl_scan(__popc(rowmask & 0xFFFFu), t, tot_lo);
-		const uint32_t p_hi = warp_excl_scan(__popc(rowmask >> 16), t, tot_hi) + tot_lo;
-		const uint32_t pre  = p_lo | (p_hi << 16);  // both at most 1024
-		while (__any_sync(FULL, m != 0)) {
-			const int      r  = m ? __ffs((int)m) - 1 : 0;
-			const uint32_t rm = __shfl_sync(FULL, rowmask, r);
-			const uint32_t pr = __shfl_sync(FULL, pre, r);
-			if (m) {
-				const uint32_t hm   = half ? (rm >> 16) : (rm & 0xFFFFu);
-				const uint32_t rank = (half ? (pr >> 16) : (pr & 0xFFFFu)) + __popc(hm & ((1u << lane) - 1));
-				const uint32_t p    = 16u * (32 * half + r) + lane;
-				store(rank, p, value_of(p));
-			}
-			m &= m - 1;
-		}
+		uint32_t       tot_lo, tot_hi;
+		const uint32_t p_lo = warp_excl_scan(__popc(pl.rowmask & 0xFFFFu), t, tot_lo);
+		const uint32_t p_hi = warp_excl_scan(__popc(pl.rowmask >> 16), t, tot_hi) + tot_lo;
+		pl.pre              = p_lo | (p_hi << 16);  // both at most 1024
 	} else {
-		uint32_t       tot;
-		const uint32_t pre = warp_excl_scan(__popc(rowmask), t, tot);
-		while (__any_sync(FULL, m != 0)) {
-			const int      r  = m ? __ffs((int)m) - 1 : 0;
-			const uint32_t rm = __shfl_sync(FULL, rowmask, r);
-			const uint32_t pr = __shfl_sync(FULL, pre, r);
-			if (m) {
-				const uint32_t rank = pr + __popc(rm & ((1u << t) - 1));
-				const uint32_t p    = 32u * r + t;
-				store(rank, p, value_of(p));
-			}
-			m &= m - 1;
+		uint32_t tot;
+		pl.pre = warp_excl_scan(__popc(pl.rowmask), t, tot);
+	}
+	return pl;
+}
+template <typename PT, int K, typename ValueOf>
+__device__ __forceinline__ void preload_exceptions(uint32_t myexc, int t, typename Traits<PT>::UT (&vals)[K], ValueOf&& value_of) {
+	uint32_t m = myexc;
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		vals[k] = 0;
+		if (m) { vals[k] = value_of((uint32_t)Map<PT>::index(t, __ffs((int)m) - 1)); }
+		m &= m - 1;
+	}
+}
+// Every thread walks ITS OWN exceptions and fetches the rank of each one's row from lane r: the loop runs
+// max-exceptions-per-thread times (2-4 for a typical vector) instead of once per row that holds an exception.
+template <typename PT, int K, typename ValueOf, typename Store>
+__device__ __forceinline__ void emit_planned(const ExcPlan& pl, uint32_t myexc, int t, const typename Traits<PT>::UT (&vals)[K > 0 ? K : 1],
+                                             ValueOf&& value_of, Store&& store) {
+	using UT = typename Traits<PT>::UT;
+	if (!pl.any) { return; }
+	uint32_t m    = myexc;
+	auto     step = [&](bool preloaded, UT pre_val) {
+        const int      r  = m ? __ffs((int)m) - 1 : 0;
+        const uint32_t rm = __shfl_sync(FULL, pl.rowmask, r);
+        const uint32_t pr = __shfl_sync(FULL, pl.pre, r);
+        if (m) {
+            uint32_t rank;
+            if (sizeof(PT) == 8) {
+                const int      lane = t & 15, half = t >> 4;
+                const uint32_t hm   = half ? (rm >> 16) : (rm & 0xFFFFu);
+                rank                = (half ? (pr >> 16) : (pr & 0xFFFFu)) + __popc(hm & ((1u << lane) - 1));
+            } else {
+                rank = pr + __popc(rm & ((1u << t) - 1));
+            }
+            const uint32_t p = (uint32_t)Map<PT>::index(t, r);
+            store(rank, p, preloaded ? pre_val : value_of(p));
+        }
+        m &= m - 1;
+	};
+	bool more = true;
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		if (more) {
+			more = __any_sync(FULL, m != 0);
+			if (more) { step(true, vals[k]); }
 		}
 	}
+	while (more && __any_sync(FULL, m != 0)) {
+		step(false, (UT)0);
+	}
+}
+template <typename PT, typename ValueOf, typename Store>
+__device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&& value_of, Store&& store) {
+	const ExcPlan                 pl      = plan_exceptions<PT>(myexc, t);
+	const typename Traits<PT>::UT none[1] = {0};
+	emit_planned<PT, 0>(pl, myexc, t, none, value_of, store);  // nothing preloaded
 }
 
 // ---- placement: in-order prefix sums over thread blocks ---------------------------------------------------------------
@@ -854,6 +898,25 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		}
 	}
 	if (staged) { fence_proxy_async_smem(); }  // generic-proxy writes to the block image -> visible to the bulk-copy engine
+	// exceptions: ranks and the first values of every thread.  Vector order: before the offsets are needed, the work hides
+	// in the placement wait (+1..5 %).  Completion order has no wait to hide it in, and carrying the values across the
+	// barrier only costs registers (-2..6 %): there the plan is made right before the emission.
+	constexpr int  EXC_PRELOAD = ORDERED ? (sizeof(PT) == 8 ? 2 : 4) : 0;
+	const uint32_t rbw         = a.bw;
+	auto           exc_value   = [&](uint32_t p) -> UT {
+        const UT bits = T::bits(in_vec[p]);
+        return rd ? (UT)(bits >> rbw) : bits;
+	};
+	ExcPlan plan;
+	plan.any     = false;
+	plan.rowmask = plan.pre = 0;
+	UT exc_first[EXC_PRELOAD > 0 ? EXC_PRELOAD : 1] = {};
+	if constexpr (ORDERED) {
+		if (active) {
+			plan = plan_exceptions<PT>(a.myexc, t);
+			if (plan.any) { preload_exceptions<PT, EXC_PRELOAD>(a.myexc, t, exc_first, exc_value); }
+		}
+	}
 	if (warp == 0) {
 		uint64_t excl = 0;
 		if constexpr (!ORDERED) {
@@ -903,19 +966,13 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(dst + 128u * a.bw), PT()); }
 	}
 	// ---- exceptions, in position order ----
-	UT*            ev  = static_cast<UT*>(col.exc_val) + exc_off;
-	uint16_t*      ep  = col.exc_pos + exc_off;
-	const uint32_t rbw = a.bw;
-	emit_exceptions<PT>(
-	    a.myexc, t,
-	    [&](uint32_t p) -> UT {
-		    const UT bits = T::bits(in_vec[p]);
-		    return rd ? (UT)(bits >> rbw) : bits;
-	    },
-	    [&](uint32_t rank, uint32_t p, UT val) {
-		    ev[rank] = val;
-		    ep[rank] = (uint16_t)p;
-	    });
+	UT*       ev = static_cast<UT*>(col.exc_val) + exc_off;
+	uint16_t* ep = col.exc_pos + exc_off;
+	if constexpr (!ORDERED) { plan = plan_exceptions<PT>(a.myexc, t); }
+	emit_planned<PT, EXC_PRELOAD>(plan, a.myexc, t, exc_first, exc_value, [&](uint32_t rank, uint32_t p, UT val) {
+		ev[rank] = val;
+		ep[rank] = (uint16_t)p;
+	});
 	// ---- the 32-byte record ----
 	if (t == 0) {
 		uint4 ra, rb;

@@ -49,19 +49,48 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
 	uint32_t       block  = col->max_block_bytes ? (uint32_t)std::min<uint64_t>(col->max_block_bytes, widest) : widest;
 	const uint32_t stage  = ((block + 127u) & ~127u) + STAGE_PAD;
-	const size_t   smem   = (size_t)DEC_WARPS * 2 * stage + DEC_WARPS * 2 * sizeof(uint64_t);
-	auto           kern   = decode_sum_kernel<PT, DEC_WARPS>;
-	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int per_sm = 0;
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_WARPS * 32, smem));
-	if (per_sm < 1) { return fail(ALPB200_ECUDA, "decode_sum: kernel does not fit on an SM"); }
-	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
-	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
-	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	// The scan is bound by what the resident warps can unpack, so the block shape is the one that puts the most warps on
+	// an SM: 8 warps per block while two stages per warp are small (narrow ALP blocks), fewer when they are wide (ALP_RD on
+	// doubles: 2 x 7.3 KiB per warp would leave ONE 8-warp block per SM; 5-warp blocks fit three).
+	ColView             view {col->meta, col->packed, col->exc_val, col->exc_pos};
 	unsigned long long* counter = di.counters + di.next_counter;
-	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
-	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_sum, stage, counter);
-	CUDA_TRY(cudaGetLastError());
+	cudaStream_t        s       = static_cast<cudaStream_t>(stream);
+	int                 best_w = 0, best_per_sm = 0;
+	auto consider = [&](auto Wc) -> int {
+		constexpr int W    = decltype(Wc)::value;
+		const size_t  smem = (size_t)W * 2 * stage + W * 2 * sizeof(uint64_t);
+		if (smem > (size_t)di.smem_optin) { return ALPB200_OK; }
+		auto kern = decode_sum_kernel<PT, W>;
+		CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		int per_sm = 0;
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem));
+		if (per_sm * W > best_per_sm * best_w) {
+			best_w      = W;
+			best_per_sm = per_sm;
+		}
+		return ALPB200_OK;
+	};
+	TRY(consider(std::integral_constant<int, 8> {}));
+	TRY(consider(std::integral_constant<int, 5> {}));
+	TRY(consider(std::integral_constant<int, 3> {}));
+	if (best_w == 0) { return fail(ALPB200_ECUDA, "decode_sum: kernel does not fit on an SM"); }
+	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+	auto launch = [&](auto Wc) -> int {
+		constexpr int  W    = decltype(Wc)::value;
+		const size_t   smem = (size_t)W * 2 * stage + W * 2 * sizeof(uint64_t);
+		const uint64_t want = (n + W - 1) / W;
+		const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * best_per_sm);
+		decode_sum_kernel<PT, W><<<grid, W * 32, smem, s>>>(view, first, n, d_sum, stage, counter);
+		CUDA_TRY(cudaGetLastError());
+		return ALPB200_OK;
+	};
+	if (best_w == 8) {
+		TRY(launch(std::integral_constant<int, 8> {}));
+	} else if (best_w == 5) {
+		TRY(launch(std::integral_constant<int, 5> {}));
+	} else {
+		TRY(launch(std::integral_constant<int, 3> {}));
+	}
 	return ALPB200_OK;
 }
 

@@ -231,6 +231,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; stdout carries the ONE JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n = (args.values // _abi.VECTOR_SIZE) * _abi.VECTOR_SIZE
     n_vec = n // _abi.VECTOR_SIZE

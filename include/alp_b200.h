@@ -151,6 +151,20 @@ int alpb200_encode_f64(const double* d_in, uint64_t n_vectors, const alpb200_rg_
                        const alpb200_column* col, void* d_workspace, void* stream);
 int alpb200_encode_f32(const float* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states,
                        const alpb200_column* col, void* d_workspace, void* stream);
+/* The general form.  flags: ALPB200_ENCODE_UNORDERED (completion-order layout, see alpb200_encode_unordered_*) and
+ * ALPB200_ENCODE_APPEND: the call CONTINUES a column — col->meta points at the record of the call's first vector (which
+ * must start a row-group; d_in and d_states point at that vector's values and row-group state), col->packed / exc_val /
+ * exc_pos / totals are those of the whole column, and the output starts where col->totals (device memory, left by the
+ * previous call on the same stream) says the column ends; totals are updated.  Appending calls give byte for byte the
+ * column one call over all vectors gives (vector-order layout) — this is how alpb200_compress_host_* overlaps the
+ * encode of one chunk with the transfers of its neighbours. */
+#define ALPB200_ENCODE_UNORDERED 1u
+#define ALPB200_ENCODE_APPEND 2u
+int alpb200_encode_ex_f64(const double* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states,
+                          const alpb200_column* col, void* d_workspace, void* stream, uint32_t flags);
+int alpb200_encode_ex_f32(const float* d_in, uint64_t n_vectors, const alpb200_rg_state* d_states,
+                          const alpb200_column* col, void* d_workspace, void* stream, uint32_t flags);
+
 /* Same encoder, COMPLETION-ORDER layout: the same per-vector blocks, exception runs and records, dense in the same
  * arrays, but handed out with one atomic per thread block instead of an in-order prefix, so blocks sit in the order
  * their thread blocks finished (roughly, not exactly, vector order) and the bytes of the column are not a pure function

@@ -413,6 +413,36 @@ def test_pipelined_host_compress_equals_one_launch(kind, n_vec):
     assert int(got.totals[3]) == int(want.totals[3])
 
 
+@pytest.mark.parametrize("kind,ordered", [(2, True), (3, True), (4, True), (2, False)])
+def test_appending_encodes_equal_one_launch(kind, ordered):
+    """alpb200_encode_ex_* with ALPB200_ENCODE_APPEND: a column encoded in three calls over consecutive row-group ranges.
+    Vector-order layout: byte for byte the column of one call.  Completion order: the same blocks, and every call's
+    blocks lie behind those of the previous calls."""
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    n_vec = 1000 + 700 + 345
+    x = pyoracle.generate(n_vec * 1024, kind)
+    xd = torch.from_numpy(x).to(_dev())
+    want = alp_b200.encode(xd).to_host()
+    col = alp_b200.DeviceColumn(n_vec, x.dtype.itemsize, _dev())
+    ends = []
+    for first, count in ((0, 1000), (1000, 700), (1700, 345)):
+        alp_b200.encode(xd[first * 1024 : (first + count) * 1024], col=col, ordered=ordered, append_at=first)
+        ends.append(col.read_totals())
+    got = col.to_host()
+    assert ends[-1] == (want.packed_bytes, want.n_exceptions)
+    if ordered:
+        _assert_columns_equal(got, want, "append")
+    else:
+        assert _blocks(got)[0] == _blocks(want)[0]
+        off = got.meta["packed_off"].astype(np.int64) * 128
+        assert off[:1000].max() < ends[0][0] <= off[1000:1700].min() and off[1000:1700].max() < ends[1][0] <= off[1700:].min()
+    assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd))
+
+
 def test_large_column_properties():
     """2^26 values (BASELINE config 2 at 1/16 scale; the full size runs in bench.py, which verifies its round trip
     too): encode→decode is the identity, sizes match the per-vector metadata, positions are sorted, blocks are dense."""

@@ -47,6 +47,12 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1)
     cols["integers<2^20 f64 (no exceptions)"] = torch.randint(0, 1 << 20, (n,), device=dev, generator=g).double()
     cols["2-decimal<100 f64 (bw 14)"] = torch.randint(0, 10000, (n,), device=dev, generator=g).double() / 100.0
+    # 0..3 decimals changing from VECTOR to vector: every row-group keeps 4 candidate (e,f) pairs, so each vector runs
+    # the second-level sampling (encoder.hpp:241-305) over them
+    kk = torch.randint(0, 1000000, (n,), device=dev, generator=g).double()
+    dd = ((torch.arange(n, device=dev) // 1024) % 5) % 4  # (period 5: the row-group sampler looks at every 12th vector)
+    cols["decimals varying per vector (k=4)"] = kk / torch.tensor([1.0, 10.0, 100.0, 1000.0], dtype=torch.float64, device=dev)[dd]
+    del kk, dd
     cols["highprec_f64 (config 3, ALP_RD)"] = alp_b200.generate(n, 3, dev)
     cols["mixed_f32 (config 4)"] = alp_b200.generate(n, 4, dev)
     print("lib", alp_b200.LIB_PATH, " values 2^%d  HBM peak %.0f GB/s (MEASURED_PEAKS.json)" % (lg, PEAK))
