@@ -156,6 +156,26 @@ __device__ __forceinline__ PT decode_value(typename Traits<PT>::ST enc, typename
 	return T::mul(T::to_float((ST)((UT)enc * (UT)fact)), frac);
 }
 
+// Helpers of the floating-point fast path of the exception test (derivation: alp_encode.cuh, "Two implementations of
+// the per-value step"): key = |product| as an unsigned integer pattern (high word for doubles), BIG = the pattern of
+// 2^63 | 2^31, fact_fp = 10^f as an exactly representable PT, cast_sat = the plain (saturating) conversion.
+template <typename PT>
+struct FastLimits;
+template <>
+struct FastLimits<double> {
+	static constexpr uint32_t BIG = 0x43E00000u;  // high word of 2^63
+	__device__ static __forceinline__ uint32_t key(double pd) { return (uint32_t)((uint64_t)__double_as_longlong(pd) >> 32) & 0x7FFFFFFFu; }
+	__device__ static __forceinline__ double fact_fp(int f) { return C_F64_EXP[f]; }  // 10^f, exact
+	__device__ static __forceinline__ int64_t cast_sat(double tr) { return __double2ll_rz(tr); }
+};
+template <>
+struct FastLimits<float> {
+	static constexpr uint32_t BIG = 0x4F000000u;  // 2^31
+	__device__ static __forceinline__ uint32_t key(float pd) { return __float_as_uint(pd) & 0x7FFFFFFFu; }
+	__device__ static __forceinline__ float fact_fp(int f) { return f < 10 ? C_F32_EXP[f] : 0.0f; }  // FACT[10] = 0 (alp_device.cuh)
+	__device__ static __forceinline__ int32_t cast_sat(float tr) { return __float2int_rz(tr); }
+};
+
 // encoder.hpp:91-107 count_bits(max, min)
 template <typename PT>
 __device__ __forceinline__ int bits_of_range(typename Traits<PT>::ST mx, typename Traits<PT>::ST mn) {

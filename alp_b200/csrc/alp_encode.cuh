@@ -216,22 +216,7 @@ struct TileIO {
 //         redoes the vector with EXACT.  For doubles the test looks at the high word only, which widens that case to
 //         2^63 <= |Pd| < 2^63 * (1 + 2^-20) — still a one-in-a-million sliver.
 //         (float, f = 10: FACT[10] is the reference's out-of-bounds 0, so P = 0 and nothing wraps; 10^f is taken as 0.)
-template <typename PT>
-struct FastLimits;
-template <>
-struct FastLimits<double> {
-	static constexpr uint32_t BIG = 0x43E00000u;  // high word of 2^63
-	__device__ static __forceinline__ uint32_t key(double pd) { return (uint32_t)((uint64_t)__double_as_longlong(pd) >> 32) & 0x7FFFFFFFu; }
-	__device__ static __forceinline__ double fact_fp(int f) { return C_F64_EXP[f]; }  // 10^f, exact
-	__device__ static __forceinline__ int64_t cast_sat(double tr) { return __double2ll_rz(tr); }
-};
-template <>
-struct FastLimits<float> {
-	static constexpr uint32_t BIG = 0x4F000000u;  // 2^31
-	__device__ static __forceinline__ uint32_t key(float pd) { return __float_as_uint(pd) & 0x7FFFFFFFu; }
-	__device__ static __forceinline__ float fact_fp(int f) { return f < 10 ? C_F32_EXP[f] : 0.0f; }  // FACT[10] = 0 (alp_device.cuh)
-	__device__ static __forceinline__ int32_t cast_sat(float tr) { return __float2int_rz(tr); }
-};
+// (FastLimits<PT>: alp_device.cuh)
 
 // what the 32 rows of a thread accumulate
 template <typename PT>

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(WARPS * 32) init_search_kernel(const PT* __res
                                                                  SearchResult* __restrict__ results) {
 	using T  = Traits<PT>;
 	using ST = typename T::ST;
+	using FL = FastLimits<PT>;
 	__shared__ PT s_smp[WARPS][32];
 	const int      warp = threadIdx.x >> 5, t = threadIdx.x & 31;
 	const uint64_t job  = (uint64_t)blockIdx.x * WARPS + warp;
@@ -63,21 +64,52 @@ __global__ void __launch_bounds__(WARPS * 32) init_search_kernel(const PT* __res
 		int e, f;
 		combo_of<T::MAX_EXP>(c, e, f);
 		const PT ex = T::exp10(e), frf = T::frac10(f), fre = T::frac10(e);
-		const ST fa = T::fact10(f);
+		const ST fa  = T::fact10(f);
+		const PT fap = FL::fact_fp(f);
 		uint32_t n_ok = 0;
-		ST       mx = T::ST_MIN, mn = T::ST_MAX;
+		ST       mx = T::ST_MIN, mn = T::ST_MAX;                   // exact path (rare)
+		PT       fmx = -T::upper_limit(), fmn = T::upper_limit();  // the encoded integers as exactly representable PT values
+		// encode_value<SAFE> turns every "impossible" scaled value (not finite, beyond +-(2^63 - 1024), or -0.0) into one
+		// sentinel integer: what that decodes to is a constant of the (e,f) pair.  Lanes hold different pairs, and for the
+		// large exponents most samples ARE impossible, so this case must not cost a divergent branch.
+		const PT sent_fp  = (PT)T::SAFE_SENTINEL;
+		const PT dec_sent = decode_value<PT>(T::SAFE_SENTINEL, fa, fre);
 #pragma unroll 4
 		for (int i = 0; i < 32; i++) {
-			const PT x   = s_smp[warp][i];
-			const ST enc = encode_value<PT, true>(x, ex, frf);
-			const PT dec = decode_value<PT>(enc, fa, fre);
-			if (dec == x) {
-				n_ok++;
-				mx = enc > mx ? enc : mx;
-				mn = enc < mn ? enc : mn;
+			const PT x = s_smp[warp][i];
+			// Same reasoning as analyze_rows<FAST> in alp_encode.cuh: while the scaled value is encodable and its product
+			// with 10^f stays below 2^63 | 2^31, (PT)(enc * FACT[f]) == t_r * 10^f; a product beyond that never decodes
+			// back; only a product of exactly that magnitude takes the literal recipe (a branch that is almost never taken).
+			const PT       t        = T::mul(T::mul(x, ex), frf);
+			const bool     possible = fabs((double)t) <= 9223372036854774784.0 && T::bits(t) != T::bits((PT)-0.0);
+			const PT       tr       = T::magic_round(t);
+			const PT       pd       = T::mul(tr, fap);
+			const uint32_t key      = FL::key(pd);
+			if (possible && key == FL::BIG) {
+				const ST enc = encode_value<PT, true>(x, ex, frf);
+				const PT dec = decode_value<PT>(enc, fa, fre);
+				if (dec == x) {
+					n_ok++;
+					mx = enc > mx ? enc : mx;
+					mn = enc < mn ? enc : mn;
+				}
+			} else {
+				const PT   dec = possible ? T::mul(pd, fre) : dec_sent;
+				const bool ok  = dec == x && (!possible || key < FL::BIG);
+				const PT   v   = possible ? tr : sent_fp;
+				if (ok) {
+					n_ok++;
+					fmx = v > fmx ? v : fmx;  // (no NaNs here: plain compares, fmax() would be an 8-instruction emulation)
+					fmn = v < fmn ? v : fmn;
+				}
 			}
 		}
 		if (n_ok < 2) { continue; }  // encoder.hpp:183
+		if (fmx >= fmn) {  // exact in PT: |t_r| < 2^63 | 2^31; the sentinel converts back to itself (float: by saturation)
+			const ST imx = FL::cast_sat(fmx), imn = FL::cast_sat(fmn);
+			mx           = imx > mx ? imx : mx;
+			mn           = imn < mn ? imn : mn;
+		}
 		const uint32_t size = 32u * bits_of_range<PT>(mx, mn) + (32u - n_ok) * (T::EXC_BITS + 16);
 		best                = min(best, (size << 8) | (uint32_t)c);
 	}

@@ -353,6 +353,42 @@ def test_host_decompress_of_a_shuffled_column(checker):
     codec.close()
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_rowgroup_init_near_the_integer_overflow_boundaries(dtype, checker):
+    """The (e,f) search of alpb200_rowgroup_init_* uses the same floating-point shortcut as the encoder; here the SAMPLED
+    values themselves sit at the boundaries (products around +-2^63 | +-2^31, impossible values, specials), many per
+    row-group.  Scheme, number of candidates and the candidate list must equal the checker's for every row-group."""
+    import torch
+
+    import alp_b200
+    from alp_b200 import _abi
+
+    rng = np.random.default_rng(21)
+    top = 63 if dtype == np.float64 else 31
+    n_rg = 48
+    span = 3000 if dtype == np.float64 else 100  # (wider float ranges fall to ALP_RD, where there is nothing to search)
+    x = np.round(rng.uniform(-span, span, size=(n_rg, 102400)), 2)
+    for rg in range(n_rg):
+        decimals, f = rg % 4, (rg * 5) % (14 if dtype == np.float64 else 8)
+        edge = (2.0**top) / (10.0**f) / (10.0**decimals)
+        cand = np.array([edge, -edge, np.nextafter(edge, 0), np.nextafter(edge, np.inf), np.floor(edge), -np.floor(edge) - 1, edge * (1 - 1e-7),
+                         edge * (1 + 1e-7), edge / 2, edge * 2, 2.0**top, -(2.0**top), 1e30, -1e30, np.inf, np.nan, -0.0, 1e-320, -1e-320])
+        hit = rng.random(102400) < (0.05 + 0.1 * (rg % 3))
+        x[rg, hit] = rng.choice(cand, size=int(hit.sum()))
+    with np.errstate(over="ignore"):
+        x = x.reshape(-1).astype(dtype)
+    n_alp = 0
+    got = alp_b200.rowgroup_init(torch.from_numpy(x).to(_dev())).cpu().numpy().view(_abi.RG_STATE_DTYPE).reshape(-1)
+    for rg in range(n_rg):
+        want = checker.init(x, rg * 102400)[0]
+        assert int(got[rg]["scheme"]) == int(want["scheme"]), rg
+        if int(want["scheme"]) == 2:
+            n_alp += 1
+            k = int(want["k"])
+            assert int(got[rg]["k"]) == k and np.array_equal(got[rg]["combos"][:k], want["combos"][:k]), (rg, got[rg]["combos"], want["combos"])
+    assert n_alp >= n_rg // 2
+
+
 def test_capacity_overflow_is_reported():
     import torch
 

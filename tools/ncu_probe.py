@@ -20,6 +20,11 @@ def main():
     if kind == "int":
         g = torch.Generator(device=dev).manual_seed(1)
         x = torch.randint(0, 1 << 20, (n,), device=dev, generator=g).double()
+    elif kind == "k4":  # 0..3 decimals changing from vector to vector: second-level sampling over 4 candidate (e,f) pairs
+        g = torch.Generator(device=dev).manual_seed(1)
+        kk = torch.randint(0, 1000000, (n,), device=dev, generator=g).double()
+        dd = ((torch.arange(n, device=dev) // 1024) % 5) % 4
+        x = kk / torch.tensor([1.0, 10.0, 100.0, 1000.0], dtype=torch.float64, device=dev)[dd]
     else:
         x = alp_b200.generate(n, int(kind), dev)
     st = alp_b200.rowgroup_init(x)
