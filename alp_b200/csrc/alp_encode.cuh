@@ -611,6 +611,28 @@ __device__ __forceinline__ void emit_planned(const ExcPlan& pl, uint32_t myexc, 
 		step(false, (UT)0);
 	}
 }
+// every thread writes the positions of its exceptions to list[rank] (shared memory)
+template <typename PT>
+__device__ __forceinline__ void file_exception_positions(const ExcPlan& pl, uint32_t myexc, int t, uint16_t* list) {
+	uint32_t m = myexc;
+	while (__any_sync(FULL, m != 0)) {
+		const int      r  = m ? __ffs((int)m) - 1 : 0;
+		const uint32_t rm = __shfl_sync(FULL, pl.rowmask, r);
+		const uint32_t pr = __shfl_sync(FULL, pl.pre, r);
+		if (m) {
+			uint32_t rank;
+			if (sizeof(PT) == 8) {
+				const int      lane = t & 15, half = t >> 4;
+				const uint32_t hm   = half ? (rm >> 16) : (rm & 0xFFFFu);
+				rank                = (half ? (pr >> 16) : (pr & 0xFFFFu)) + __popc(hm & ((1u << lane) - 1));
+			} else {
+				rank = pr + __popc(rm & ((1u << t) - 1));
+			}
+			list[rank] = (uint16_t)Map<PT>::index(t, r);
+		}
+		m &= m - 1;
+	}
+}
 template <typename PT, typename ValueOf, typename Store>
 __device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&& value_of, Store&& store) {
 	const ExcPlan                 pl      = plan_exceptions<PT>(myexc, t);
@@ -883,23 +905,30 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		}
 	}
 	if (staged) { fence_proxy_async_smem(); }  // generic-proxy writes to the block image -> visible to the bulk-copy engine
-	// exceptions: ranks and the first values of every thread.  Vector order: before the offsets are needed, the work hides
-	// in the placement wait (+1..5 %).  Completion order has no wait to hide it in, and carrying the values across the
-	// barrier only costs registers (-2..6 %): there the plan is made right before the emission.
-	constexpr int  EXC_PRELOAD = ORDERED ? (sizeof(PT) == 8 ? 2 : 4) : 0;
-	const uint32_t rbw         = a.bw;
-	auto           exc_value   = [&](uint32_t p) -> UT {
+	// Exceptions.  Their ranks (position order) come from a bit-matrix transpose of the per-thread bitmaps and two warp
+	// scans; walking them is a loop over the exceptions of the busiest thread.  When the part of the tile behind the block
+	// image has room (2 bytes per exception), every thread FILES the positions of its exceptions at their ranks there —
+	// shuffles and shared-memory stores only, and all of it before the output offset is needed — and the emission after
+	// the wait is a coalesced loop: 32 consecutive ranks per step, 32 independent loads of the original values in flight,
+	// contiguous stores.  (Walking the exceptions thread by thread with one dependent L2 load per step was what kept
+	// exception-heavy columns — 90-150 per vector — at 0.42-0.49 of the roofline.)  Otherwise: emit_planned.
+	const uint32_t rbw       = a.bw;
+	auto           exc_value = [&](uint32_t p) -> UT {
         const UT bits = T::bits(in_vec[p]);
         return rd ? (UT)(bits >> rbw) : bits;
 	};
 	ExcPlan plan;
 	plan.any     = false;
 	plan.rowmask = plan.pre = 0;
-	UT exc_first[EXC_PRELOAD > 0 ? EXC_PRELOAD : 1] = {};
-	if constexpr (ORDERED) {
-		if (active) {
-			plan = plan_exceptions<PT>(a.myexc, t);
-			if (plan.any) { preload_exceptions<PT, EXC_PRELOAD>(a.myexc, t, exc_first, exc_value); }
+	uint16_t* pos_list = reinterpret_cast<uint16_t*>(mine + bytes);
+	bool      listed   = false;  // warp-uniform
+	if (active) {
+		plan   = plan_exceptions<PT>(a.myexc, t);
+		listed = staged && plan.any && Cfg::SMEM_PER_WARP - bytes >= 2u * a.cnt;
+		if (listed) {
+			__syncwarp();  // every lane is done reading its rows of the tile (32-bit lanes pack without a warp-wide sync)
+			file_exception_positions<PT>(plan, a.myexc, t, pos_list);
+			__syncwarp();
 		}
 	}
 	if (warp == 0) {
@@ -953,11 +982,19 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	// ---- exceptions, in position order ----
 	UT*       ev = static_cast<UT*>(col.exc_val) + exc_off;
 	uint16_t* ep = col.exc_pos + exc_off;
-	if constexpr (!ORDERED) { plan = plan_exceptions<PT>(a.myexc, t); }
-	emit_planned<PT, EXC_PRELOAD>(plan, a.myexc, t, exc_first, exc_value, [&](uint32_t rank, uint32_t p, UT val) {
-		ev[rank] = val;
-		ep[rank] = (uint16_t)p;
-	});
+	if (listed) {
+		for (uint32_t i = t; i < a.cnt; i += 32) {
+			const uint32_t p = pos_list[i];
+			ev[i]            = exc_value(p);
+			ep[i]            = (uint16_t)p;
+		}
+	} else {
+		const UT none[1] = {0};
+		emit_planned<PT, 0>(plan, a.myexc, t, none, exc_value, [&](uint32_t rank, uint32_t p, UT val) {
+			ev[rank] = val;
+			ep[rank] = (uint16_t)p;
+		});
+	}
 	// ---- the 32-byte record ----
 	if (t == 0) {
 		uint4 ra, rb;
