@@ -231,9 +231,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; stdout carries the ONE JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION / WARN / INFO, possibly from /etc/nccl.conf) on stdout unless
+        # told where else to log; stdout carries the ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n = (args.values // _abi.VECTOR_SIZE) * _abi.VECTOR_SIZE
     n_vec = n // _abi.VECTOR_SIZE

@@ -431,6 +431,65 @@ def test_host_codec_round_trip(kind, checker):
     codec.close()
 
 
+@pytest.mark.parametrize("kind,log2n", [(2, 30), (3, 30), (4, 28)])
+def test_baseline_configs_at_full_size(kind, log2n, checker, port):
+    """BASELINE.json configs 2-4 at their FULL sizes (2^30 f64 / 2^28 f32 values), through size-independent properties:
+    encode -> decode is the identity (bit patterns, plus an XOR checksum of checksums), the metadata is consistent with
+    the totals (dense offsets in vector order), both layouts hold the same blocks, the fused SUM agrees with the decoded
+    column, and slices from the start, the middle and the ragged end of the column are byte-identical to what the CPU
+    checker makes of the same values."""
+    import torch
+
+    import alp_b200
+    from alp_b200 import _abi
+    from oracle import pyoracle
+
+    n = 1 << log2n
+    xd = alp_b200.generate(n, kind, _dev())
+    col = alp_b200.encode(xd)
+    packed_bytes, n_exc = col.read_totals()
+    y = alp_b200.decode(col)
+    ib = torch.int64 if xd.element_size() == 8 else torch.int32
+    assert torch.equal(y.view(ib), xd.view(ib))
+
+    def xor_all(t):  # tree reduction of the bit patterns: a checksum of (chunk) checksums
+        t = t.view(ib).clone()
+        while t.numel() > 1:
+            h = t.numel() // 2
+            t = t[:h] ^ t[h : 2 * h] if t.numel() % 2 == 0 else torch.cat([t[:h] ^ t[h : 2 * h], t[2 * h :]])
+        return int(t.item())
+
+    assert xor_all(y) == xor_all(xd)
+    want_sum = float(y.double().sum().item())
+    del y
+    meta = col.meta.cpu().numpy().view(_abi.VEC_META_DTYPE).reshape(-1)
+    units = np.where(meta["scheme"] == 1, meta["bw"].astype(np.int64) + meta["e"], meta["bw"].astype(np.int64))
+    cnt = meta["exc_cnt"].astype(np.int64)
+    assert packed_bytes == int(units.sum()) * 128 and n_exc == int(cnt.sum())
+    assert np.array_equal(meta["packed_off"].astype(np.int64), np.concatenate([[0], np.cumsum(units)[:-1]]))
+    assert np.array_equal(meta["exc_off"].astype(np.int64), np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+    assert set(meta["scheme"].tolist()) == ({1} if kind == 3 else {2})
+    got_sum = float(alp_b200.decode_sum(col).item())
+    assert abs(got_sum - want_sum) <= 1e-9 * max(1.0, abs(want_sum))
+    # slices against the CPU checker: first row-groups, a middle range, the short last row-group
+    n_vec = n // 1024
+    for first, count in ((0, 200), (n_vec // 2 // 100 * 100, 300), (n_vec // 100 * 100, n_vec % 100)):
+        if count == 0:
+            continue
+        host = pyoracle.generate(count * 1024, kind, first_index=first * 1024)
+        assert host.tobytes() == xd[first * 1024 : (first + count) * 1024].cpu().numpy().tobytes()
+        judge = port if kind == 3 else checker
+        _assert_columns_equal(col.to_host(first, count), judge.encode_column(host, n_threads=8), "full-size slice %d" % first)
+    # the completion-order layout of the same column: same totals, same records apart from the offsets
+    un = alp_b200.encode(xd, ordered=False)
+    assert un.read_totals() == (packed_bytes, n_exc)
+    um = un.meta.cpu().numpy().view(_abi.VEC_META_DTYPE).reshape(-1)
+    for key in ("exc_cnt", "scheme", "bw", "e", "f"):
+        assert np.array_equal(um[key], meta[key]), key
+    z = alp_b200.decode(un)
+    assert torch.equal(z.view(ib), xd.view(ib))
+
+
 @pytest.mark.parametrize("kind,n_vec", [(2, 16 * 1000 + 3 * 100 + 41), (3, 2300), (4, 40 * 100)])
 def test_pipelined_host_compress_equals_one_launch(kind, n_vec):
     """alpb200_compress_host pipelines the column in chunks of whole row-groups whose encodes APPEND to the column; the
