@@ -110,53 +110,10 @@ __device__ __forceinline__ void choose_exponent_factor(PT xs, const StateRegs& s
 	f_out = best_f;
 }
 
-// ---- value access policies -------------------------------------------------------------------------------------------
+// ---- value access policy ----------------------------------------------------------------------------------------------
 // The analysis and packing code reads row r of the thread's 32 rows through an IO policy with a compile-time row
-// number.  GlobalIO streams the vector from global memory in double-buffered batches of 8 rows (every warp load
-// instruction covers full 128-byte lines); TileIO works on a shared-memory copy of the vector (value order) and can
-// store the encoded integers back — used by the single-vector primitives, which must return them.
-template <typename PT>
-struct GlobalIO {
-	using UT = typename Traits<PT>::UT;
-	static constexpr int B = 8;
-	const PT* in;
-	int       t;
-	UT        cur[B], nxt[B];
-	__device__ __forceinline__ GlobalIO(const PT* in_vec, int lane_id) : in(in_vec), t(lane_id) {
-#pragma unroll
-		for (int i = 0; i < B; i++) {
-			nxt[i] = Traits<PT>::bits(in[Map<PT>::index(t, i)]);
-		}
-	}
-	template <int R>
-	__device__ __forceinline__ UT load(std::integral_constant<int, R>) {
-		if constexpr (R % B == 0) {
-#pragma unroll
-			for (int i = 0; i < B; i++) {
-				cur[i] = nxt[i];
-			}
-			if constexpr (R + B < 32) {
-#pragma unroll
-				for (int i = 0; i < B; i++) {
-					nxt[i] = Traits<PT>::bits(in[Map<PT>::index(t, R + B + i)]);
-				}
-			}
-		}
-		return cur[R % B];
-	}
-	template <int R>
-	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT) {}
-	// value i of the vector (second-level sampling)
-	__device__ __forceinline__ PT sample(const PT* in_vec, int i) const { return in_vec[i]; }
-	// start over (the analysis is redone with the exact per-value recipe)
-	__device__ __forceinline__ void rewind(const PT* in_vec) {
-#pragma unroll
-		for (int i = 0; i < B; i++) {
-			nxt[i] = Traits<PT>::bits(in_vec[Map<PT>::index(t, i)]);
-		}
-	}
-	static constexpr bool KEEPS = false;  // encoded integers are not kept anywhere
-};
+// number.  TileIO works on a shared-memory copy of the vector (value order) and stores the encoded integers back in
+// place — the batched kernel's tile (filled by a bulk-async copy) and the single-vector primitives' tile alike.
 template <typename PT>
 struct TileIO {
 	using UT = typename Traits<PT>::UT;
@@ -180,7 +137,7 @@ struct TileIO {
 			tile[Map<PT>::index(t, r)] = Traits<PT>::bits(in_vec[Map<PT>::index(t, r)]);
 		}
 	}
-	static constexpr bool KEEPS = true;  // the tile holds the encoded integers afterwards
+	// the encoded integer stored for value `position`
 	__device__ __forceinline__ UT kept(int position) const { return tile[position]; }
 };
 
@@ -225,8 +182,6 @@ struct RowAcc {
 	uint32_t myexc  = 0;
 	uint32_t lo_min = 0xFFFFFFFFu, lo_max = 0, hi_and = 0xFFFFFFFFu, hi_or = 0;  // f64
 	ST       mn = Traits<PT>::ST_MAX, mx = Traits<PT>::ST_MIN;                   // f32
-	ST       first  = 0;            // encoded integer of this thread's first non-exception
-	uint32_t unseen = 0xFFFFFFFFu;  // all-ones until the thread has met a non-exception
 };
 
 // One pass over the thread's 32 rows.  Returns false (FAST only) when some lane met a value on the boundary described above.
@@ -260,11 +215,6 @@ __device__ __forceinline__ bool analyze_rows(IO& io, int e, int f, RowAcc<PT>& a
 		}
 		io.store(R, (UT)enc);
 		if (exc) { acc.myexc |= 1u << r; }
-		if constexpr (!IO::KEEPS) {
-			const uint32_t em = exc ? 0xFFFFFFFFu : 0u;
-			acc.first         = (acc.unseen & ~em) ? enc : acc.first;
-			acc.unseen &= em;
-		}
 		if (!exc) {  // exceptions take no part in min / max (predicated, no branch)
 			if constexpr (sizeof(PT) == 8) {
 				const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
@@ -306,13 +256,9 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 	cand   = __reduce_min_sync(FULL, cand);
 	a.fill = 0;
 	if (cand != 0xFFFFu) {
-		const int owner = Map<PT>::thread_of((int)cand);
-		if constexpr (IO::KEEPS) {
-			__syncwarp();
-			a.fill = (ST)io.kept((int)cand);
-		}
+		__syncwarp();  // another lane stored it
+		a.fill = (ST)io.kept((int)cand);
 		if constexpr (sizeof(PT) == 8) {
-			if constexpr (!IO::KEEPS) { a.fill = (ST)shfl_u64((uint64_t)acc.first, owner); }
 			const uint32_t hi_and = __reduce_and_sync(FULL, acc.hi_and);
 			const uint32_t hi_or  = __reduce_or_sync(FULL, acc.hi_or);
 			if (hi_and == hi_or) {  // one common high word: order is decided by the low words
@@ -332,7 +278,6 @@ __device__ __forceinline__ void analyze_alp(const PT* __restrict__ in_vec, const
 				mx = warp_max<ST>(mx);
 			}
 		} else {
-			if constexpr (!IO::KEEPS) { a.fill = (ST)__shfl_sync(FULL, (int)acc.first, owner); }
 			mn     = warp_min<ST>(mn);
 			mx     = warp_max<ST>(mx);
 		}
@@ -472,30 +417,6 @@ __device__ __forceinline__ void pack_rows_inplace(uint32_t* tile, uint32_t myexc
 	pack_rows(tile, myexc, fill, base, bw, t, reinterpret_cast<uint8_t*>(tile));
 }
 
-// ---- second pass of the batched encoder: FFOR straight from the input ------------------------------------------------
-// Re-reads the vector (L2-resident: this warp streamed it a moment ago), re-encodes it with the chosen (e,f) — no
-// decode/compare, the exception bitmap is known — and packs.  dst may be shared or global memory.
-// (not inlined: keeps the 33 width instances out of the kernel body)
-static __device__ __noinline__ void pack_from_input(const float* __restrict__ in_vec, uint32_t bw, uint32_t e, uint32_t f, uint32_t base,
-                                             uint32_t fill, uint32_t myexc, bool rd, int t, uint8_t* __restrict__ dst) {
-	using T = Traits<float>;
-	const float ex = T::exp10(rd ? 0 : e), frf = T::frac10(rd ? 0 : f);
-	if (rd) { myexc = 0; }
-	dispatch_width<0, 32>(bw, [&](auto W) {
-		constexpr int BW = decltype(W)::value;
-		if constexpr (BW > 0) {
-			GlobalIO<float> io(in_vec, t);
-			pack32_rows<BW>(t, reinterpret_cast<uint32_t*>(dst), [&](auto R) -> uint32_t {
-				constexpr int  r    = decltype(R)::value;
-				const uint32_t bits = io.load(R);
-				uint32_t       v    = rd ? bits : (uint32_t)encode_value<float, false>(T::from_bits(bits), ex, frf);
-				if ((myexc >> r) & 1u) { v = fill; }
-				return v - base;
-			});
-		}
-	});
-}
-
 __device__ __forceinline__ uint32_t nib(const uint32_t (&n)[4], int r) { return (n[r >> 3] >> (4 * (r & 7))) & 0xFu; }
 
 // pack the ALP_RD dictionary indices on 16-bit lanes (64 lanes x 16 rows): value v = 64*row16 + lane16
@@ -534,10 +455,8 @@ __device__ __forceinline__ void pack_left(const uint32_t (&left_nib)[4], uint32_
 }
 
 // ---- exception emission in position order (encoder.hpp:390-397 / rd.hpp:138-142) ------------------------------------
-// Split in two so that the batched encoder can do everything that does not need the output offset BEFORE it waits for
-// it: plan_exceptions (ranks: a 32x32 bit-matrix transpose of the per-thread bitmaps and two warp scans) and
-// preload_exceptions (the first K values of every thread, fetched with independent loads instead of one L2 round trip
-// per loop iteration).  emit_planned then only shuffles and stores.
+// plan_exceptions computes the ranks: a 32x32 bit-matrix transpose of the per-thread bitmaps and two warp scans — nothing
+// that needs the output offset, so the batched encoder does it before it waits for that offset.
 //   value_of(p) returns what is stored for position p (the original value for ALP, the left part for ALP_RD).
 struct ExcPlan {
 	uint32_t rowmask;  // lane r: ballot of "is exception" over the threads' row r
@@ -563,57 +482,12 @@ __device__ __forceinline__ ExcPlan plan_exceptions(uint32_t myexc, int t) {
 	}
 	return pl;
 }
-template <typename PT, int K, typename ValueOf>
-__device__ __forceinline__ void preload_exceptions(uint32_t myexc, int t, typename Traits<PT>::UT (&vals)[K], ValueOf&& value_of) {
-	uint32_t m = myexc;
-#pragma unroll
-	for (int k = 0; k < K; k++) {
-		vals[k] = 0;
-		if (m) { vals[k] = value_of((uint32_t)Map<PT>::index(t, __ffs((int)m) - 1)); }
-		m &= m - 1;
-	}
-}
 // Every thread walks ITS OWN exceptions and fetches the rank of each one's row from lane r: the loop runs
 // max-exceptions-per-thread times (2-4 for a typical vector) instead of once per row that holds an exception.
-template <typename PT, int K, typename ValueOf, typename Store>
-__device__ __forceinline__ void emit_planned(const ExcPlan& pl, uint32_t myexc, int t, const typename Traits<PT>::UT (&vals)[K > 0 ? K : 1],
-                                             ValueOf&& value_of, Store&& store) {
-	using UT = typename Traits<PT>::UT;
+// visit(rank, position) is called once per exception.
+template <typename PT, typename Visit>
+__device__ __forceinline__ void for_each_exception(const ExcPlan& pl, uint32_t myexc, int t, Visit&& visit) {
 	if (!pl.any) { return; }
-	uint32_t m    = myexc;
-	auto     step = [&](bool preloaded, UT pre_val) {
-        const int      r  = m ? __ffs((int)m) - 1 : 0;
-        const uint32_t rm = __shfl_sync(FULL, pl.rowmask, r);
-        const uint32_t pr = __shfl_sync(FULL, pl.pre, r);
-        if (m) {
-            uint32_t rank;
-            if (sizeof(PT) == 8) {
-                const int      lane = t & 15, half = t >> 4;
-                const uint32_t hm   = half ? (rm >> 16) : (rm & 0xFFFFu);
-                rank                = (half ? (pr >> 16) : (pr & 0xFFFFu)) + __popc(hm & ((1u << lane) - 1));
-            } else {
-                rank = pr + __popc(rm & ((1u << t) - 1));
-            }
-            const uint32_t p = (uint32_t)Map<PT>::index(t, r);
-            store(rank, p, preloaded ? pre_val : value_of(p));
-        }
-        m &= m - 1;
-	};
-	bool more = true;
-#pragma unroll
-	for (int k = 0; k < K; k++) {
-		if (more) {
-			more = __any_sync(FULL, m != 0);
-			if (more) { step(true, vals[k]); }
-		}
-	}
-	while (more && __any_sync(FULL, m != 0)) {
-		step(false, (UT)0);
-	}
-}
-// every thread writes the positions of its exceptions to list[rank] (shared memory)
-template <typename PT>
-__device__ __forceinline__ void file_exception_positions(const ExcPlan& pl, uint32_t myexc, int t, uint16_t* list) {
 	uint32_t m = myexc;
 	while (__any_sync(FULL, m != 0)) {
 		const int      r  = m ? __ffs((int)m) - 1 : 0;
@@ -628,16 +502,15 @@ __device__ __forceinline__ void file_exception_positions(const ExcPlan& pl, uint
 			} else {
 				rank = pr + __popc(rm & ((1u << t) - 1));
 			}
-			list[rank] = (uint16_t)Map<PT>::index(t, r);
+			visit(rank, (uint32_t)Map<PT>::index(t, r));
 		}
 		m &= m - 1;
 	}
 }
 template <typename PT, typename ValueOf, typename Store>
 __device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&& value_of, Store&& store) {
-	const ExcPlan                 pl      = plan_exceptions<PT>(myexc, t);
-	const typename Traits<PT>::UT none[1] = {0};
-	emit_planned<PT, 0>(pl, myexc, t, none, value_of, store);  // nothing preloaded
+	const ExcPlan pl = plan_exceptions<PT>(myexc, t);
+	for_each_exception<PT>(pl, myexc, t, [&](uint32_t rank, uint32_t p) { store(rank, p, value_of(p)); });
 }
 
 // ---- placement: in-order prefix sums over thread blocks ---------------------------------------------------------------
@@ -750,11 +623,6 @@ struct ColOut {
 // ORDERED = false (alpb200_encode_unordered_*): one atomicAdd hands out the space, so blocks land in COMPLETION order:
 //                  the same blocks, the same records (offsets differ), dense, but not sorted by vector.
 //
-// ALPB200_ENC_F32_TWO_PASS=1 selects the previous f32 strategy (kept for comparison): pass 1 analyses from global
-// memory without staging, pass 2 re-reads the vector (L2), re-encodes and FFORs into a per-warp stage.
-#ifndef ALPB200_ENC_F32_TWO_PASS
-#define ALPB200_ENC_F32_TWO_PASS 0
-#endif
 #ifndef ALPB200_ENC_SPIN_NS
 #define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth)
 #endif
@@ -762,7 +630,6 @@ template <typename PT>
 struct EncodeCfg;
 template <>
 struct EncodeCfg<double> {
-	static constexpr bool     TWO_PASS      = false;
 	static constexpr uint32_t SMEM_PER_WARP = VEC * sizeof(double);  // the tile
 	static constexpr uint32_t INPLACE_MAX   = 32;                    // widest block packed in place
 	// 9 warps x 3 blocks = 27 warps per SM: what 227 KiB of shared memory hold at 8 KiB a vector (72 registers per thread).
@@ -772,7 +639,6 @@ struct EncodeCfg<double> {
 };
 template <>
 struct EncodeCfg<float> {
-	static constexpr bool     TWO_PASS      = ALPB200_ENC_F32_TWO_PASS != 0;
 	static constexpr uint32_t SMEM_PER_WARP = 35 * 128u;  // tile (32 units); every f32 block fits: 32 bits, or ALP_RD 31 + 3
 	static constexpr uint32_t INPLACE_MAX   = 32;
 	static constexpr int      WARPS         = 8;
@@ -808,7 +674,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	}
 	const uint64_t v      = (uint64_t)bid * WARPS + warp;
 	const bool     active = v < n_vectors;
-	uint8_t*       mine   = smem + (size_t)warp * Cfg::SMEM_PER_WARP;  // the tile (two-pass f32: the packed-block stage)
+	uint8_t*       mine   = smem + (size_t)warp * Cfg::SMEM_PER_WARP;  // the tile
 	UT*            tile   = reinterpret_cast<UT*>(mine);
 
 	Analysis<PT> a;
@@ -821,33 +687,22 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	uint32_t                units  = 0;
 	bool                    rd     = false;
 	if (active) {
-		if constexpr (!Cfg::TWO_PASS) {
-			// the whole input vector (contiguous) arrives in the tile with one bulk-async copy (TMA 1-D)
-			if (t == 0) {
-				mbar_init(&s_bar[warp], 1);
-				fence_mbar_init();
-				mbar_arrive_expect_tx(&s_bar[warp], VEC * sizeof(PT));
-				bulk_g2s(tile, in_vec, VEC * sizeof(PT), &s_bar[warp]);
-			}
+		// the whole input vector (contiguous) arrives in the tile with one bulk-async copy (TMA 1-D)
+		if (t == 0) {
+			mbar_init(&s_bar[warp], 1);
+			fence_mbar_init();
+			mbar_arrive_expect_tx(&s_bar[warp], VEC * sizeof(PT));
+			bulk_g2s(tile, in_vec, VEC * sizeof(PT), &s_bar[warp]);
 		}
 		st = load_state(state);
 		rd = st.scheme == ALPB200_SCHEME_ALP_RD;
-		if constexpr (!Cfg::TWO_PASS) {
-			__syncwarp();
-			mbar_wait(&s_bar[warp], 0);
-			TileIO<PT> io(tile, t);
-			if (rd) {
-				analyze_rd<PT>(state, st, t, io, a, [](int, uint32_t) {});
-			} else {
-				analyze_alp<PT>(in_vec, st, t, io, a);
-			}
+		__syncwarp();
+		mbar_wait(&s_bar[warp], 0);
+		TileIO<PT> io(tile, t);
+		if (rd) {
+			analyze_rd<PT>(state, st, t, io, a, [](int, uint32_t) {});
 		} else {
-			GlobalIO<PT> io(in_vec, t);
-			if (rd) {
-				analyze_rd<PT>(state, st, t, io, a, [](int, uint32_t) {});
-			} else {
-				analyze_alp<PT>(in_vec, st, t, io, a);
-			}
+			analyze_alp<PT>(in_vec, st, t, io, a);
 		}
 		units = rd ? a.bw + a.e : a.bw;
 	}
@@ -887,22 +742,14 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	const uint32_t bytes = units * 128u;
 	// ---- step 4: build the packed block image in shared memory while the scanner works out this block's offsets ----
 	bool staged = false;  // warp-uniform: the block sits at `mine`, ready for a bulk store
-	if constexpr (Cfg::TWO_PASS) {
-		if (active) {
-			pack_from_input(in_vec, a.bw, a.e, a.f, (UT)a.base, (UT)a.fill, a.myexc, rd, t, mine);
-			if (rd) { pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(mine + 128u * a.bw), PT()); }
-			staged = true;
+	if (active && a.bw <= Cfg::INPLACE_MAX) {
+		__syncwarp();  // the tile is complete (analysis stored to it lane by lane)
+		pack_rows_inplace(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t);
+		if (rd) {  // only 32-bit lanes get here: the index block follows the right parts
+			__syncwarp();
+			pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(mine + 128u * a.bw), PT());
 		}
-	} else {
-		if (active && a.bw <= Cfg::INPLACE_MAX) {
-			__syncwarp();  // the tile is complete (analysis stored to it lane by lane)
-			pack_rows_inplace(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t);
-			if (rd) {  // only 32-bit lanes get here: the index block follows the right parts
-				__syncwarp();
-				pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(mine + 128u * a.bw), PT());
-			}
-			staged = true;
-		}
+		staged = true;
 	}
 	if (staged) { fence_proxy_async_smem(); }  // generic-proxy writes to the block image -> visible to the bulk-copy engine
 	// Exceptions.  Their ranks (position order) come from a bit-matrix transpose of the per-thread bitmaps and two warp
@@ -911,7 +758,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	// shuffles and shared-memory stores only, and all of it before the output offset is needed — and the emission after
 	// the wait is a coalesced loop: 32 consecutive ranks per step, 32 independent loads of the original values in flight,
 	// contiguous stores.  (Walking the exceptions thread by thread with one dependent L2 load per step was what kept
-	// exception-heavy columns — 90-150 per vector — at 0.42-0.49 of the roofline.)  Otherwise: emit_planned.
+	// exception-heavy columns — 90-150 per vector — at 0.42-0.49 of the roofline.)  Otherwise the values are fetched and stored inside that walk.
 	const uint32_t rbw       = a.bw;
 	auto           exc_value = [&](uint32_t p) -> UT {
         const UT bits = T::bits(in_vec[p]);
@@ -927,7 +774,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		listed = staged && plan.any && Cfg::SMEM_PER_WARP - bytes >= 2u * a.cnt;
 		if (listed) {
 			__syncwarp();  // every lane is done reading its rows of the tile (32-bit lanes pack without a warp-wide sync)
-			file_exception_positions<PT>(plan, a.myexc, t, pos_list);
+			for_each_exception<PT>(plan, a.myexc, t, [&](uint32_t rank, uint32_t p) { pos_list[rank] = (uint16_t)p; });
 			__syncwarp();
 		}
 	}
@@ -989,9 +836,8 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 			ep[i]            = (uint16_t)p;
 		}
 	} else {
-		const UT none[1] = {0};
-		emit_planned<PT, 0>(plan, a.myexc, t, none, exc_value, [&](uint32_t rank, uint32_t p, UT val) {
-			ev[rank] = val;
+		for_each_exception<PT>(plan, a.myexc, t, [&](uint32_t rank, uint32_t p) {
+			ev[rank] = exc_value(p);
 			ep[rank] = (uint16_t)p;
 		});
 	}

@@ -135,7 +135,7 @@ __device__ __forceinline__ void window_put(uint32_t (&w)[NW], uint32_t x) {
 //                image of one half of a lane overlaps rows the other half has not read yet).
 template <int BW, bool DEFER = false, typename Produce>
 __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, Produce&& produce) {
-	uint32_t w[BW + 1];
+	uint32_t w[BW + 1] = {};  // (every word is assigned before it is read; the initialiser only tells the front end so)
 	// BW even: pair m = words (2m, 2m+1) -> element 16*(half*BW/2 + m) + lane.
 	// BW odd : half 0 owns stream words 0..BW-1, half 1 words BW..2BW-1, so pairs start one word later for half 1:
 	//          pair m = half ? (2m+1, 2m+2) : (2m, 2m+1) -> element 16*((half ? (BW+1)/2 : 0) + m) + lane, and element
@@ -182,7 +182,7 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, P
 // produced, and element 32*i + t is the slot of this very thread's row i.
 template <int BW, typename Produce>
 __device__ __forceinline__ void pack32_rows(int t, uint32_t* dst, Produce&& produce) {
-	uint32_t w[BW + 1];
+	uint32_t w[BW + 1] = {};  // (every word is assigned before it is read; the initialiser only tells the front end so)
 	static_for<0, 32>([&](auto R) {
 		constexpr int r = decltype(R)::value;
 		window_put<BW + 1, r * BW, BW>(w, produce(R));
