@@ -16,6 +16,12 @@ Printed JSON (rank 0, one line):
   e2e        the same metric through the host-buffer API (alpb200_decompress_host): pinned host column in,
              pinned host values out, copies inside the timed region
   cpu_baseline  the reference's CPU decode (oracle/_ref, all host threads) on a bounded slice of the same column
+Beside the contract's keys (reported, not the headline):
+  encode        device-timed alpb200_encode_f64 of the same column (vector-order layout, the default) with its roofline
+                fraction, the completion-order layout beside it, and the row-group init
+  scan_sum      fused decode + SUM (alpb200_decode_sum_f64), bound by the compressed read
+  e2e_scan      SUM over the pinned host column through alpb200_sum_host_f64 (only compressed bytes cross PCIe)
+  e2e_compress  pinned host values in, pinned host column out through alpb200_compress_host_f64
 """
 import argparse
 import json
