@@ -101,3 +101,19 @@ def test_reference_own_unit_test_passes_on_the_shim(golden_vectors):
     assert res.returncode == 0, tail
     assert "[  PASSED  ] 6 tests." in res.stdout, tail
     assert res.stdout.count("[       OK ]") == 6, tail
+
+
+def test_reference_own_unit_test_fails_loudly_without_gpu(golden_vectors):
+    """The same binary on a machine without a GPU: every case must FAIL with the shim's gpu_error — a silent CPU path
+    behind the reference's API would let it pass."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not os.path.exists(REF_TEST):
+        pytest.skip("oracle/_ref/ref_test_on_shim not built (needs /root/reference at build time)")
+    _materialise_reference_fixtures(golden_vectors)
+    res = subprocess.run([REF_TEST], capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0
+    assert "[  PASSED  ] 0 tests." in res.stdout and res.stdout.count("[  FAILED  ]") >= 6
+    assert "no CUDA device" in res.stdout or "gpu_error" in res.stdout or "CUDA" in res.stdout, res.stdout[-1500:]
