@@ -394,20 +394,32 @@ __device__ __forceinline__ void pack_rows(const uint32_t* tile, uint32_t myexc, 
 
 // FFOR IN PLACE: the tile of encoded integers becomes the packed block image (bytes [0, 128*bw) of the tile), ready to
 // leave with one bulk-async store.  Runs BEFORE the block's output offset is known, i.e. it overlaps the placement wait.
-// 64-bit lanes, bw <= 32 only (wider blocks keep more words live than the register budget allows; they take the
-// direct path).  Only the low words are read: (v - base) mod 2^32 is all a field of <= 32 bits needs.
+// 64-bit lanes: bw <= 32 keeps every word in registers until the warp has read the whole tile and reads only the low
+// words ((v - base) mod 2^32 is all a field of <= 32 bits needs); wider blocks defer just the words that would land on
+// unread rows (alp_ffor.cuh, PACK_INPLACE_WIDE).
 __device__ __forceinline__ void pack_rows_inplace(uint64_t* tile, uint32_t myexc, uint64_t fill, uint64_t base, uint32_t bw, int t) {
 	const int       lane = t & 15, half = t >> 4;
 	const uint32_t* lo32 = reinterpret_cast<const uint32_t*>(tile);
-	dispatch_width<0, 32>(bw, [&](auto W) {
+	dispatch_width<0, 64>(bw, [&](auto W) {
 		constexpr int BW = decltype(W)::value;
-		if constexpr (BW > 0) {
-			pack64_rows<BW, true>(lane, half, tile, [&](auto R, uint32_t& lo, uint32_t& hi) {
+		if constexpr (BW == 0) {
+			return;
+		} else if constexpr (BW <= 32) {
+			pack64_rows<BW, PACK_INPLACE_NARROW>(lane, half, tile, [&](auto R, uint32_t& lo, uint32_t& hi) {
 				constexpr int r = decltype(R)::value;
 				uint32_t      v = lo32[2 * Map<double>::index(t, r)];
 				if ((myexc >> r) & 1u) { v = (uint32_t)fill; }
 				lo = v - (uint32_t)base;
 				hi = 0;
+			});
+		} else {
+			pack64_rows<BW, PACK_INPLACE_WIDE>(lane, half, tile, [&](auto R, uint32_t& lo, uint32_t& hi) {
+				constexpr int r = decltype(R)::value;
+				uint64_t      v = tile[Map<double>::index(t, r)];
+				if ((myexc >> r) & 1u) { v = fill; }
+				const uint64_t d = v - base;  // masked to BW bits by the packer
+				lo               = (uint32_t)d;
+				hi               = (uint32_t)(d >> 32);
 			});
 		}
 	});
@@ -631,7 +643,7 @@ struct EncodeCfg;
 template <>
 struct EncodeCfg<double> {
 	static constexpr uint32_t SMEM_PER_WARP = VEC * sizeof(double);  // the tile
-	static constexpr uint32_t INPLACE_MAX   = 32;                    // widest block packed in place
+	static constexpr uint32_t INPLACE_MAX   = SMEM_PER_WARP;         // largest block (bytes) packed in place: whatever fits the tile
 	// 9 warps x 3 blocks = 27 warps per SM: what 227 KiB of shared memory hold at 8 KiB a vector (72 registers per thread).
 	// Measured against 8 x 3 (80 registers): 2-3 % faster.
 	static constexpr int      WARPS         = 9;
@@ -640,7 +652,7 @@ struct EncodeCfg<double> {
 template <>
 struct EncodeCfg<float> {
 	static constexpr uint32_t SMEM_PER_WARP = 35 * 128u;  // tile (32 units); every f32 block fits: 32 bits, or ALP_RD 31 + 3
-	static constexpr uint32_t INPLACE_MAX   = 32;
+	static constexpr uint32_t INPLACE_MAX   = SMEM_PER_WARP;
 	static constexpr int      WARPS         = 8;
 	static constexpr int      WARPS_PER_SM  = 32;  // 4.4 KiB and 64 registers
 };
@@ -742,10 +754,13 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	const uint32_t bytes = units * 128u;
 	// ---- step 4: build the packed block image in shared memory while the scanner works out this block's offsets ----
 	bool staged = false;  // warp-uniform: the block sits at `mine`, ready for a bulk store
-	if (active && a.bw <= Cfg::INPLACE_MAX) {
+	// (An ALP_RD block of 63 + 3 or 62 + 3 units on doubles would outgrow the tile.  Completion order has no wait to fill:
+	// there wide blocks are better off with the direct line stores — 1.74 vs 1.80 ms per 2^29 on the ALP_RD column; with
+	// the wait, packing in place first wins, 1.99 vs 2.05 ms.)
+	if (active && bytes <= Cfg::INPLACE_MAX && (ORDERED || a.bw <= 32)) {
 		__syncwarp();  // the tile is complete (analysis stored to it lane by lane)
 		pack_rows_inplace(tile, rd ? 0u : a.myexc, (UT)a.fill, (UT)a.base, a.bw, t);
-		if (rd) {  // only 32-bit lanes get here: the index block follows the right parts
+		if (rd) {  // the index block follows the right parts
 			__syncwarp();
 			pack_left(a.left_nib, a.e, t, reinterpret_cast<uint16_t*>(mine + 128u * a.bw), PT());
 		}

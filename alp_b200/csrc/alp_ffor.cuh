@@ -129,18 +129,29 @@ __device__ __forceinline__ void window_put(uint32_t (&w)[NW], uint32_t x) {
 }
 
 // 64-bit lanes.  produce(R, lo, hi) yields the (unmasked) field of row R::value; dst = the block as 64-bit elements.
-// DEFER = false: words are stored as soon as they are complete (all positions are compile-time), so only a few stay live.
-// DEFER = true : every word stays in registers until all 32 rows have been produced and the whole warp has passed a
-//                __syncwarp() — for packing IN PLACE, where dst aliases the memory that produce() reads (the block
-//                image of one half of a lane overlaps rows the other half has not read yet).
-template <int BW, bool DEFER = false, typename Produce>
+// MODE 0 (PACK_DIRECT): words are stored as soon as they are complete (all positions are compile-time), so only a few
+//                       stay live.  dst must not alias what produce() reads.
+// MODE 1 (PACK_INPLACE_NARROW, BW <= 32): packing IN PLACE — dst is the [row][lane] tile produce() reads.  The block
+//                       image of half 1 lands on rows half 0 has not read yet, so every word stays in registers until
+//                       all 32 rows have been produced and the whole warp has passed a __syncwarp().
+// MODE 2 (PACK_INPLACE_WIDE, BW > 32): in place with at most 2*(32 - BW/2) words deferred.  Half 0 writes element
+//                       16*m + lane, the slot of its own row m, which it has consumed by the time pair m is complete
+//                       (BW <= 64): immediate.  Half 1 writes element 16*(B1 + m) + lane, B1 = ceil(BW/2): below
+//                       element 512 that is a row of half 0 (deferred until after the __syncwarp()), from 512 on it is
+//                       its own row B1 + m - 32 <= m, already consumed: immediate.
+constexpr int PACK_DIRECT = 0, PACK_INPLACE_NARROW = 1, PACK_INPLACE_WIDE = 2;
+template <int BW, int MODE = PACK_DIRECT, typename Produce>
 __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, Produce&& produce) {
+	static_assert(MODE != PACK_INPLACE_NARROW || BW <= 32, "narrow in-place packing keeps every word in registers");
 	uint32_t w[BW + 1] = {};  // (every word is assigned before it is read; the initialiser only tells the front end so)
 	// BW even: pair m = words (2m, 2m+1) -> element 16*(half*BW/2 + m) + lane.
 	// BW odd : half 0 owns stream words 0..BW-1, half 1 words BW..2BW-1, so pairs start one word later for half 1:
 	//          pair m = half ? (2m+1, 2m+2) : (2m, 2m+1) -> element 16*((half ? (BW+1)/2 : 0) + m) + lane, and element
 	//          (BW-1)/2 is shared: last word of half 0 (low) + first word of half 1 (high), completed with one shuffle.
-	uint64_t* p = dst + 16 * ((BW & 1) ? (half ? (BW + 1) / 2 : 0) : half * (BW / 2)) + lane;
+	constexpr int B1      = (BW + 1) / 2;                                   // first element row of half 1's pairs
+	constexpr int N_PAIRS = (BW & 1) ? (BW - 1) / 2 : BW / 2;               // per half
+	constexpr int N_LATE  = MODE == PACK_INPLACE_NARROW ? N_PAIRS : (MODE == PACK_INPLACE_WIDE ? (32 - B1 > 0 ? (32 - B1 < N_PAIRS ? 32 - B1 : N_PAIRS) : 0) : 0);
+	uint64_t*     p       = dst + 16 * ((BW & 1) ? (half ? B1 : 0) : half * (BW / 2)) + lane;
 	auto store_pair = [&](auto Mc) {
 		constexpr int m = decltype(Mc)::value;
 		if constexpr ((BW & 1) == 0) {
@@ -160,16 +171,29 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, P
 			window_put<BW + 1, r * BW, 32>(w, lo);
 			window_put<BW + 1, r * BW + 32, BW - 32>(w, hi);
 		}
-		if constexpr (!DEFER) {
+		if constexpr (MODE != PACK_INPLACE_NARROW) {
 			constexpr int done_before = (r * BW) >> 5, done_now = ((r + 1) * BW) >> 5;  // complete words
 			constexpr int pairs_before = (BW & 1) ? (done_before > 0 ? (done_before - 1) / 2 : 0) : done_before / 2;
 			constexpr int pairs_now    = (BW & 1) ? (done_now > 0 ? (done_now - 1) / 2 : 0) : done_now / 2;
-			static_for<pairs_before, pairs_now>(store_pair);
+			static_for<pairs_before, pairs_now>([&](auto Mc) {
+				constexpr int m = decltype(Mc)::value;
+				if constexpr (MODE == PACK_INPLACE_WIDE && m < N_LATE) {
+					if (half == 0) { store_pair(Mc); }  // half 1's pair m would land on a row half 0 still has to read
+				} else {
+					store_pair(Mc);
+				}
+			});
 		}
 	});
-	if constexpr (DEFER) {
+	if constexpr (MODE != PACK_DIRECT) {
 		__syncwarp();  // every lane has read all of its rows
-		static_for<0, (BW & 1) ? (BW - 1) / 2 : BW / 2>(store_pair);
+		if constexpr (MODE == PACK_INPLACE_NARROW) {
+			static_for<0, N_LATE>(store_pair);
+		} else {
+			static_for<0, N_LATE>([&](auto Mc) {
+				if (half == 1) { store_pair(Mc); }
+			});
+		}
 	}
 	if constexpr (BW & 1) {
 		const uint32_t other = __shfl_xor_sync(FULL, half ? w[0] : w[BW - 1], 16);

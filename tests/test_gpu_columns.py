@@ -389,6 +389,51 @@ def test_rowgroup_init_near_the_integer_overflow_boundaries(dtype, checker):
     assert n_alp >= n_rg // 2
 
 
+@pytest.mark.parametrize("ordered", [True, False])
+def test_rd_every_right_width_with_given_states(ordered, checker):
+    """ALP_RD through the batched encoder for EVERY cut position (right widths 48..63) and index width 1..3, with
+    hand-made row-group states: in-place packing of wide blocks (only the words that would land on unread rows are
+    deferred), the direct path where block + index block outgrow the tile (62+3, 63+2, 63+3), left-part exceptions.
+    The decoder (independent, width-specialised unpack) and the CPU checker must both give the values back, and the
+    right-part blocks must equal the single-vector primitive's FFOR of the same right parts."""
+    import torch
+
+    import alp_b200
+    from alp_b200 import _abi
+    from alp_b200 import primitives as gpu
+
+    rng = np.random.default_rng(17)
+    combos = [(rbw, lbw) for rbw in range(48, 64) for lbw in (1, 2, 3)]
+    states = np.zeros(len(combos), dtype=_abi.RG_STATE_DTYPE)
+    parts = []
+    for i, (rbw, lbw) in enumerate(combos):
+        ds = 1 << lbw if lbw > 1 else 2
+        dict_vals = rng.choice(1 << (64 - rbw), size=min(ds, 1 << (64 - rbw)), replace=False).astype(np.uint64)
+        ds = dict_vals.size
+        states[i]["scheme"], states[i]["right_bw"], states[i]["left_bw"], states[i]["dict_size"] = 1, rbw, lbw, ds
+        states[i]["dict"][:ds] = dict_vals.astype(np.uint16)
+        left = dict_vals[rng.integers(0, ds, size=102400)]
+        stray = rng.random(102400) < 0.01  # left parts outside the dictionary: exceptions
+        left[stray] = rng.integers(0, 1 << (64 - rbw), size=int(stray.sum()), dtype=np.uint64)
+        right = rng.integers(0, 1 << 62, size=102400, dtype=np.uint64) & np.uint64((1 << rbw) - 1)
+        parts.append((left << np.uint64(rbw)) | right)
+    bits = np.concatenate(parts)
+    x = bits.view(np.float64)
+    xd = torch.from_numpy(x).to(_dev())
+    sd = torch.from_numpy(states.view(np.uint8).reshape(len(states), -1)).to(_dev())
+    col = alp_b200.encode(xd, sd, ordered=ordered)
+    col.read_totals()
+    assert torch.equal(_bits(alp_b200.decode(col)), _bits(xd))
+    h = col.to_host()
+    assert checker.decode_column(h, n_threads=8).tobytes() == x.tobytes()
+    assert np.array_equal(h.meta["bw"][::100], np.array([c[0] for c in combos], dtype=np.uint8))
+    for i, (rbw, lbw) in enumerate(combos):  # one vector per state against the primitive path (FFOR straight to memory)
+        v = i * 100 + 3
+        want = gpu.ffor(bits[v * 1024 : (v + 1) * 1024] & np.uint64((1 << rbw) - 1), rbw, 0)
+        p0 = int(h.meta["packed_off"][v]) * 128
+        assert h.packed[p0 : p0 + 128 * rbw].tobytes() == want.tobytes(), (rbw, lbw)
+
+
 def test_capacity_overflow_is_reported():
     import torch
 
