@@ -163,11 +163,26 @@ def cpu_decode_baseline(col_host, n_threads, budget_s, checker):
     return n_values * 8.0 * reps / dt / 1e9, reps, dt
 
 
+class JsonChannel:
+    """The process's real stdout, reserved for the ONE JSON line: file descriptor 1 is pointed at stderr for everything
+    else (NCCL prints a version banner on stdout when the box sets NCCL_DEBUG, libraries print progress, ...)."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        self._out.write(json.dumps(obj) + "\n")
+        self._out.flush()
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU decode (falp + patch_exceptions) on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    channel = JsonChannel()
     from oracle import pyoracle
 
     checker = pyoracle.best()
@@ -206,7 +221,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    channel.emit(line)
 
 
 def main():
@@ -224,6 +239,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    channel = JsonChannel()
     import torch
     import torch.distributed as dist
 
@@ -237,9 +253,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION / WARN / INFO, possibly from /etc/nccl.conf) on stdout unless
-        # told where else to log; stdout carries the ONE JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n = (args.values // _abi.VECTOR_SIZE) * _abi.VECTOR_SIZE
     n_vec = n // _abi.VECTOR_SIZE
@@ -488,7 +501,7 @@ def main():
                 "roofline_frac": read_bytes / (scan_ms * 1e-3) / 1e9 / peak,
             },
         }
-        print(json.dumps(line))
+        channel.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
