@@ -199,8 +199,10 @@ int alpb200_decode_sum_f32(const alpb200_column* col, uint64_t first_vector, uin
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host engine calls; copies are part of the call).
- * A codec context owns device staging buffers, pinned bounce buffers and streams so that repeated
- * calls do not allocate.
+ * A codec context owns device staging buffers, a small pinned area and three streams so that repeated
+ * calls do not allocate; every call pipelines the column in ~16 chunks (transfers of neighbouring chunks overlap the
+ * kernels of the current one) and returns when the result is complete.  A context serves ONE call at a time: use one
+ * context per host thread (they may share a device).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct alpb200_ctx alpb200_ctx;
 
