@@ -93,8 +93,11 @@ typedef struct alpb200_vec_meta {
 
 /*
  * Column container (struct of arrays; device pointers for the batched entry points, host pointers for
- * the *_host entry points and for the CPU oracle).  Exceptions of all vectors are concatenated in vector
- * order: exc_val[exc_off + i] / exc_pos[exc_off + i].  exc_val elements have the width of the column
+ * the *_host entry points and for the CPU oracle).  A vector's packed block starts at packed + 128 * packed_off,
+ * its exceptions are exc_val[exc_off + i] / exc_pos[exc_off + i], i < exc_cnt, positions ascending.  Blocks and
+ * exception runs are dense; alpb200_encode_* places them in VECTOR ORDER (any vector range is one byte range),
+ * alpb200_encode_unordered_* in completion order — readers must go through the offsets, and every reader in this
+ * library does.  exc_val elements have the width of the column
  * type (8 bytes f64, 4 bytes f32); an ALP_RD vector stores its 16-bit left-part exceptions zero-extended
  * in the same slots.
  */
