@@ -201,6 +201,9 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     value = n_sample * 8.0 / (ms * 1e-3) / 1e9
+    t0 = time.perf_counter()
+    checker.decode_column(col, n_threads=1, out=out)  # the reference's own methodology is single-core
+    one_thread = n_sample * 8.0 / (time.perf_counter() - t0) / 1e9
     sample = "2^%d values of the same column, all vectors, decode = falp + patch_exceptions" % int(np.log2(n_sample))
     line = {
         "impl": "reference",
@@ -217,7 +220,8 @@ def run_reference(args):
         "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_values": n_sample, "host_threads": threads},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": checker.kind, "sample": sample, "build": checker.build_info},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": checker.kind, "sample": sample, "build": checker.build_info,
+                         "single_thread_value": one_thread},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -429,11 +433,13 @@ def main():
         sl = col.to_host(0, n_slice_vec)
         threads = host_threads()
         gbps, reps, dt = cpu_decode_baseline(sl, threads, args.cpu_seconds, checker)
+        one_gbps, _, _ = cpu_decode_baseline(sl, 1, 1.0, checker)
         cpu = {
             "value": gbps,
             "unit": UNIT,
             "cores": threads,
             "kind": checker.kind,
+            "single_thread_value": one_gbps,
             "sample": "first 2^%d values of the same column decoded %d times in %.1f s (falp + patch_exceptions, %s)" % (int(np.log2(n_slice_vec * 1024)), reps, dt, checker.build_info),
         }
 
