@@ -247,25 +247,9 @@ def test_encode_near_the_integer_overflow_boundaries(dtype, checker):
 
     import alp_b200
 
-    rng = np.random.default_rng(5)
-    top = 63 if dtype == np.float64 else 31
-    parts = []
-    for decimals in (0, 1, 2, 3, 5):
-        scale = 10.0**decimals
-        base = np.round(rng.uniform(-5000, 5000, size=(100, 1024)), decimals)
-        for f in range(0, 14 if dtype == np.float64 else 8):
-            # x * 10^decimals * 10^f ~ 2^top: the products enc * 10^f of these land on both sides of the wrap
-            edge = (2.0**top) / (10.0**f) / scale
-            cand = np.array([edge, -edge, np.nextafter(edge, 0), np.nextafter(edge, np.inf), edge * (1 - 1e-7), edge * (1 + 1e-7),
-                             np.floor(edge), np.floor(edge) + 1, -np.floor(edge) - 1, edge / 2, edge * 2, edge * 0.999, edge * 1.001])
-            rows = rng.integers(0, 100, size=cand.size)
-            cols = rng.integers(0, 1024, size=cand.size)
-            base[rows, cols] = cand
-        special = np.array([2.0**top, -(2.0**top), 2.0**top * 1.5, -(2.0**top) * 1.5, 1e30, -1e30, np.inf, -np.inf, np.nan, -0.0, 2.0 ** (top - 1)])
-        base[rng.integers(0, 100, size=special.size), rng.integers(0, 1024, size=special.size)] = special
-        parts.append(base.reshape(-1))
-    with np.errstate(over="ignore"):
-        x = np.concatenate(parts).astype(dtype)
+    from conftest import overflow_boundary_column
+
+    x = overflow_boundary_column(dtype, np.random.default_rng(5))
     xd = torch.from_numpy(x).to(_dev())
     col = alp_b200.encode(xd)
     h = col.to_host()

@@ -227,3 +227,24 @@ def test_column_drivers_agree(reference, port):
         assert a.exc_val[: a.n_exceptions].tobytes() == b.exc_val[: b.n_exceptions].tobytes()
         assert reference.decode_column(b, n_threads=2).tobytes() == x.tobytes()
         assert port.decode_column(a, n_threads=2).tobytes() == x.tobytes()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_port_matches_reference_at_the_integer_overflow_boundaries(dtype, reference, port):
+    """The column the GPU encoder's fast path is checked on (tests/test_gpu_columns.py): the C restatement and the
+    compiled reference must agree on it byte for byte — x86 cast of out-of-range values, wrapping integer products, the
+    SAFE sentinel in the sampling — so that either can be the judge."""
+    from conftest import overflow_boundary_column
+
+    x = overflow_boundary_column(dtype, np.random.default_rng(5))
+    a, b = port.encode_column(x, n_threads=4), reference.encode_column(x, n_threads=4)
+    alp = b.meta["scheme"] == 2
+    assert alp.any() and np.array_equal(a.meta["scheme"], b.meta["scheme"])
+    for key in ("exc_cnt", "bw", "e", "f"):
+        assert np.array_equal(a.meta[key][alp], b.meta[key][alp]), key
+    assert np.array_equal(a.meta["base"][alp], b.meta["base"][alp])
+    if alp.all():
+        assert a.packed[: a.packed_bytes].tobytes() == b.packed[: b.packed_bytes].tobytes()
+        assert a.exc_val[: a.n_exceptions].tobytes() == b.exc_val[: b.n_exceptions].tobytes()
+        assert a.exc_pos[: a.n_exceptions].tobytes() == b.exc_pos[: b.n_exceptions].tobytes()
+    assert port.decode_column(b, n_threads=4).tobytes() == x.tobytes() and reference.decode_column(a, n_threads=4).tobytes() == x.tobytes()
