@@ -126,14 +126,22 @@ class DeviceColumn:
         return view
 
 
-def rowgroup_init(values):
-    """alp::encoder<PT>::init (+ rd_encoder<PT>::init) for every row-group of a device column → uint8 [n_rg, 1196]."""
+def rowgroup_init(values, states=None, workspace=None):
+    """alp::encoder<PT>::init (+ rd_encoder<PT>::init) for every row-group of a device column → uint8 [n_rg, 1196].
+    `states` / `workspace` let a caller reuse its buffers (nothing is allocated then)."""
     _require_cuda(values, "values")
     vb = values.element_size()
     n = values.numel()
     n_rg = max(1, -(-(n // _abi.VECTOR_SIZE) // _abi.ROWGROUP_VECTORS))
-    states = torch.empty((n_rg, _abi.RG_STATE_DTYPE.itemsize), dtype=torch.uint8, device=values.device)
-    ws = torch.empty(max(256, lib.alpb200_init_workspace_bytes(n)), dtype=torch.uint8, device=values.device)
+    if states is None:
+        states = torch.empty((n_rg, _abi.RG_STATE_DTYPE.itemsize), dtype=torch.uint8, device=values.device)
+    _require_cuda(states, "states")
+    if states.numel() < n_rg * _abi.RG_STATE_DTYPE.itemsize:
+        raise ValueError("states holds fewer than %d row-group records" % n_rg)
+    need = max(256, lib.alpb200_init_workspace_bytes(n))
+    ws = torch.empty(need, dtype=torch.uint8, device=values.device) if workspace is None else workspace
+    if ws.numel() < need:
+        raise ValueError("workspace is smaller than alpb200_init_workspace_bytes(n)")
     with torch.cuda.device(values.device):
         fn = getattr(lib, "alpb200_rowgroup_init_" + _sfx(vb))
         check(fn(values.data_ptr(), n, states.data_ptr(), ws.data_ptr(), _stream_ptr(values.device)))
@@ -159,6 +167,7 @@ def encode(values, states=None, col=None, workspace=None, ordered=True, append_a
         col = DeviceColumn(n_vec, vb, values.device)
     if workspace is None:
         workspace = torch.empty(max(256, lib.alpb200_encode_workspace_bytes(n_vec)), dtype=torch.uint8, device=values.device)
+    col.max_block_bytes = 0  # the decode hint of whatever this column held before is stale now (read_totals() renews it)
     st = col.as_struct()
     flags = 0 if ordered else 1
     if append_at is not None:

@@ -9,19 +9,22 @@ f64 values (<= 3 decimals; SURVEY.md §8d generator, seed 42) per GPU, already c
 timed region starts.  N > 1 (torchrun, one rank per GPU) shards the global column by whole row-groups: rank r owns
 values [r*2^30, (r+1)*2^30); there is no data-path collective, so scaling is weak.
 
-Printed JSON (rank 0, one line):
+Printed JSON (rank 0, one line) — the contract's keys:
   value      decoded GB/s (uncompressed f64 bytes produced per second), whole job, device-timed with CUDA events
   roofline   algorithmic HBM bytes (compressed bytes read + decoded bytes written, summed from the column's own
              per-vector metadata) / measured kernel time, against the measured copy bandwidth of MEASURED_PEAKS.json
-  e2e        the same metric through the host-buffer API (alpb200_decompress_host): pinned host column in,
-             pinned host values out, copies inside the timed region
+  e2e        the same metric through the host-buffer API (alpb200_decompress_host): pinned host column in, pinned host
+             values out, copies inside the timed region; `link` = pinned-copy bandwidths measured in the same run at the
+             same N (all ranks at once), `link_frac` = the time the two copies need at those rates / the measured time
   cpu_baseline  the reference's CPU decode (oracle/_ref, all host threads) on a bounded slice of the same column
-Beside the contract's keys (reported, not the headline):
-  encode        device-timed alpb200_encode_f64 of the same column (vector-order layout, the default) with its roofline
-                fraction, the completion-order layout beside it, and the row-group init
-  scan_sum      fused decode + SUM (alpb200_decode_sum_f64), bound by the compressed read
-  e2e_scan      SUM over the pinned host column through alpb200_sum_host_f64 (only compressed bytes cross PCIe)
-  e2e_compress  pinned host values in, pinned host column out through alpb200_compress_host_f64
+and beside them (reported, not the headline):
+  configs    one block per BASELINE config 2 / 3 / 4 (decimal f64, high-precision f64 = ALP_RD, mixed f32): decode,
+             encode (vector order and completion order), row-group init, init + encode, fused decode + SUM — each
+             device-timed with its roofline fraction and a bit-exact check — and, at N = 1, the reference's CPU decode /
+             encode / scan on a bounded slice of the same column (`cpu`)
+  e2e_scan / e2e_compress   SUM over the pinned host column (alpb200_sum_host_f64) and host values in -> host column out
+             (alpb200_compress_host_f64), with the reference's CPU rate for the same job beside them
+  scatter    N > 1: rank 0 hands its compressed column out as row-group shards over NCCL (outside the timed region)
 """
 import argparse
 import json
@@ -43,6 +46,13 @@ UNIT = "GB/s"
 KIND = 2  # decimal-heavy f64
 DEFAULT_VALUES = 1 << 30
 WORKLOAD = "alp_decode 2^30 synthetic decimal-heavy f64 (<=3 decimals) per GPU, 1024-value vectors"
+# BASELINE.json configs measured beside the headline: kind -> (label, value bytes, values relative to --values)
+SIDE_CONFIGS = {
+    2: ("config 2: decimal-heavy f64 (ALP)", 8, 1.0),
+    3: ("config 3: high-precision f64 (ALP_RD)", 8, 1.0),
+    4: ("config 4: mixed decimal / exception f32 (ALP)", 4, 0.25),
+}
+CPU_SAMPLE_VALUES = 1 << 27  # bounded sample of a column for the CPU legs
 
 
 def host_threads():
@@ -59,6 +69,17 @@ def measured_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(n_values):
+    """The `config` object: what the workload IS — identical in both arms (the driver compares them)."""
+    return {
+        "workload": WORKLOAD,
+        "values_per_gpu": int(n_values),
+        "vectors_per_gpu": int(n_values // 1024),
+        "generator": "splitmix64 seed 42, k mod 10^6 / 10^d, d = (i / 102400) mod 4 (SURVEY.md section 8d)",
+        "l2": "inputs larger than L2 / LLC (about 2.75 B/value compressed in, 8 B/value out per step)",
+    }
 
 
 class ClockSampler:
@@ -115,13 +136,6 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": sm_max, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def pinned(shape, dtype):
-    import torch
-
-    t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name) if np.dtype(dtype).kind == "f" else torch.uint8, pin_memory=True)
-    return t
-
-
 def pinned_host_column(h):
     """Copy of a HostColumn whose arrays are page-locked (what a host engine would hand to the codec)."""
     import torch
@@ -148,19 +162,71 @@ def pinned_host_column(h):
     return out
 
 
-def cpu_decode_baseline(col_host, n_threads, budget_s, checker):
-    """Time the CPU checker's decode of a host column, repeated until `budget_s` seconds have passed."""
-    n_values = col_host.n_vectors * 1024
-    out = np.empty(n_values, dtype=np.float64)
-    checker.decode_column(col_host, n_threads=n_threads, out=out)  # warm-up (page faults, caches)
+def algorithmic_read_bytes(meta, value_bytes):
+    """Compressed bytes a decode reads, SURVEY.md §8d, summed from the column's own per-vector records: ALP vectors
+    128*bw + header (bw, e, f, count, base = 13 / 9 B) + (S+2) B per exception; ALP_RD vectors 128*(right_bw + left_bw)
+    + 4-byte header + 4 B per exception, plus the 16-byte dictionary once per row-group."""
+    alp = meta["scheme"] == 2
+    bw = meta["bw"].astype(np.int64)
+    exc = meta["exc_cnt"].astype(np.int64)
+    alp_bytes = int((128 * bw[alp] + (5 + value_bytes) + (value_bytes + 2) * exc[alp]).sum())
+    rd_bytes = int((128 * (bw[~alp] + meta["e"][~alp].astype(np.int64)) + 4 + 4 * exc[~alp]).sum())
+    rd_groups = int((~alp)[::100].sum())
+    return alp_bytes + rd_bytes + 16 * rd_groups
+
+
+def time_cpu(fn, budget_s, max_reps=50):
+    """Seconds per call of fn(): one warm-up, then repeated until `budget_s` has passed (at least once)."""
+    fn()
     reps, t0 = 0, time.perf_counter()
     while True:
-        checker.decode_column(col_host, n_threads=n_threads, out=out)
+        fn()
         reps += 1
         dt = time.perf_counter() - t0
-        if dt >= budget_s or reps >= 200:
-            break
-    return n_values * 8.0 * reps / dt / 1e9, reps, dt
+        if dt >= budget_s or reps >= max_reps:
+            return dt / reps, reps
+
+
+def cpu_legs(checker, x_host, threads, budget_s, ref_col=None):
+    """The reference's CPU path on a host sample of a column, all host threads: decode (falp + patch_exceptions, or
+    unffor x2 + rd decode), encode with given states (encode + analyze_ffor + ffor / rd encode + 2x ffor,
+    test/test_alp_sample.cpp:141-145,164-166), row-group init + encode, and the scan query (alp_func + aggr_plus,
+    q1.cpp:63-100).  GB/s are bytes of uncompressed values per second."""
+    from alp_b200 import _abi
+
+    n = x_host.shape[0] // 1024 * 1024
+    x_host = x_host[:n]
+    vb = x_host.dtype.itemsize
+    nbytes = n * vb
+    units = 67 if vb == 8 else 35
+    col = _abi.HostColumn(n // 1024, vb, (n // 1024 + threads * 100) * units * 128, n + threads * 102400)
+    states = checker.bench_init(x_host, n_threads=threads)
+    t_init, _ = time_cpu(lambda: checker.bench_init(x_host, n_threads=threads, states=states), budget_s / 4)
+    t_enc, _ = time_cpu(lambda: checker.bench_encode(x_host, n_threads=threads, states=states, col=col), budget_s / 4)
+    out = np.empty(n, dtype=x_host.dtype)
+    t_dec, reps = time_cpu(lambda: checker.decode_column(col, n_threads=threads, out=out), budget_s / 4, 200)
+    ok = out.tobytes() == x_host.tobytes()
+    got = [0.0]
+
+    def scan():
+        got[0] = checker.sum_column(col, n_threads=threads)
+
+    t_scan, _ = time_cpu(scan, budget_s / 4)
+    t_dec1, _ = time_cpu(lambda: checker.decode_column(col, n=min(col.n_vectors, 4096), n_threads=1, out=out), 0.3)
+    return {
+        "cores": threads,
+        "kind": checker.kind,
+        "sample": "first 2^%.2f values of the same column (%s)" % (np.log2(max(n, 1)), checker.build_info),
+        "round_trip_bit_exact": bool(ok),
+        "decode_GBps": nbytes / t_dec / 1e9,
+        "decode_reps": reps,
+        "decode_single_thread_GBps": min(col.n_vectors, 4096) * 1024 * vb / t_dec1 / 1e9,
+        "encode_GBps": nbytes / t_enc / 1e9,
+        "rowgroup_init_ms": t_init * 1e3,
+        "init_plus_encode_GBps": nbytes / (t_enc + t_init) / 1e9,
+        "scan_sum_GBps": nbytes / t_scan / 1e9,
+        "scan_sum": got[0],
+    }
 
 
 class JsonChannel:
@@ -178,33 +244,38 @@ class JsonChannel:
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU decode (falp + patch_exceptions) on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores — the headline is its
+    decode (falp + patch_exceptions) of the SAME 2^30-value column; encode / scan and configs 3 / 4 ride along."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     channel = JsonChannel()
-    from oracle import pyoracle
+    from oracle import pyoracle  # loads only oracle/ libraries: this arm never maps libalp_b200.so
 
     checker = pyoracle.best()
     threads = host_threads()
-    n_sample = min(args.values, 1 << 27)  # bounded sample of the same workload
-    x = pyoracle.generate(n_sample, KIND)
-    col = checker.encode_column(x, n_threads=threads, packed_capacity=n_sample * 4, exc_capacity=n_sample // 8)
-    out = np.empty(n_sample, dtype=np.float64)
+    n = args.values // 1024 * 1024
+    x = pyoracle.generate(n, KIND, n_threads=threads)
+    col = checker.bench_encode(x, n_threads=threads)  # untimed set-up: the compressed column (init + encode per row-group)
+    out = np.empty(n, dtype=np.float64)
     for _ in range(max(1, args.warmup)):
         checker.decode_column(col, n_threads=threads, out=out)
-    assert out.tobytes() == x.tobytes()
+    verified = out.tobytes() == x.tobytes()
+    assert verified, "the reference's decode of its own column differs from the original"
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
         checker.decode_column(col, n_threads=threads, out=out)
         times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
-    value = n_sample * 8.0 / (ms * 1e-3) / 1e9
-    t0 = time.perf_counter()
-    checker.decode_column(col, n_threads=1, out=out)  # the reference's own methodology is single-core (SURVEY.md section 6)
-    one_thread = n_sample * 8.0 / (time.perf_counter() - t0) / 1e9
-    sample = "2^%d values of the same column, all vectors, decode = falp + patch_exceptions" % int(np.log2(n_sample))
+    value = n * 8.0 / (ms * 1e-3) / 1e9
+    del out, col
+    side = {}
+    for kind, (label, vb, rel) in SIDE_CONFIGS.items():
+        ns = int(min(n * rel, CPU_SAMPLE_VALUES)) // 1024 * 1024
+        xs = x[:ns] if kind == KIND else pyoracle.generate(ns, kind, n_threads=threads)
+        side[str(kind)] = dict(cpu_legs(checker, xs, threads, args.cpu_seconds / 3), label=label)
+    sample = "the whole 2^%.2f-value column, all vectors, decode = falp + patch_exceptions" % np.log2(max(n, 1))
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -219,13 +290,179 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_values": n_sample, "host_threads": threads},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": checker.kind, "sample": sample, "build": checker.build_info,
-                         "single_thread_value": one_thread},
+        "config": workload_config(n),
+        "verified_bit_exact": bool(verified),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": checker.kind, "sample": sample, "build": checker.build_info},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "configs": side,
     }
     channel.emit(line)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------------
+def cuda_ms(fn, reps):
+    """Average device time of fn() over `reps` launches (CUDA events on torch's current stream, which is the stream
+    the library launches on)."""
+    import torch
+
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def compress_on_device(x, dev, reps=3):
+    """Row-group init + encode of a device column, device-timed -> (trimmed DeviceColumn, timings dict)."""
+    import torch
+
+    import alp_b200
+
+    vb = x.element_size()
+    n_vec = x.numel() // 1024
+    big = alp_b200.DeviceColumn(n_vec, vb, dev)  # worst-case capacities; allocated before anything is timed
+    ws = torch.empty(max(256, alp_b200.lib.alpb200_encode_workspace_bytes(n_vec)), dtype=torch.uint8, device=dev)
+    states = alp_b200.rowgroup_init(x)
+    alp_b200.encode(x, states, col=big, workspace=ws)  # warm-up (also first touch of the output buffers)
+    alp_b200.encode(x, states, col=big, workspace=ws, ordered=False)
+    n_rg = states.shape[0]
+    init_ws = torch.empty(max(256, alp_b200.lib.alpb200_init_workspace_bytes(x.numel())), dtype=torch.uint8, device=dev)
+    t = {}
+    t["encode_unordered_ms"] = cuda_ms(lambda: alp_b200.encode(x, states, col=big, workspace=ws, ordered=False), reps)
+    t["rowgroup_init_ms"] = cuda_ms(lambda: alp_b200.rowgroup_init(x, states=states, workspace=init_ws), reps)
+    t["encode_ms"] = cuda_ms(lambda: alp_b200.encode(x, states, col=big, workspace=ws), reps)  # vector order: the column used below
+
+    def both():
+        alp_b200.rowgroup_init(x, states=states, workspace=init_ws)
+        alp_b200.encode(x, states, col=big, workspace=ws)
+
+    t["init_plus_encode_ms"] = cuda_ms(both, reps)
+    t["row_groups"] = int(n_rg)
+    packed_bytes, n_exc = big.read_totals()
+    col = alp_b200.DeviceColumn(n_vec, vb, dev, max(packed_bytes, 128), max(n_exc, 1))  # trimmed to what was used
+    col.meta.copy_(big.meta)
+    col.packed[:packed_bytes].copy_(big.packed[:packed_bytes])
+    col.exc_val[:n_exc].copy_(big.exc_val[:n_exc])
+    col.exc_pos[:n_exc].copy_(big.exc_pos[:n_exc])
+    col.totals.copy_(big.totals)
+    col.max_block_bytes = big.max_block_bytes
+    del big, ws, states, init_ws
+    torch.cuda.empty_cache()
+    return col, t
+
+
+def config_block(kind, n, dev, rank, peak, steps, cpu_checker, cpu_seconds):
+    """One BASELINE config on this rank's GPU: device-timed encode / init / decode / scan with roofline fractions and a
+    bit-exact check; at N = 1 the reference's CPU numbers for a bounded slice of the same column beside them."""
+    import torch
+
+    import alp_b200
+    from alp_b200 import _abi
+
+    label, vb, _ = SIDE_CONFIGS[kind]
+    x = alp_b200.generate(n, kind, dev, first_index=rank * n)
+    col, t = compress_on_device(x, dev)
+    meta = col.meta.cpu().numpy().view(_abi.VEC_META_DTYPE).reshape(-1)
+    read_bytes = algorithmic_read_bytes(meta, vb)
+    algo = read_bytes + n * vb
+    out = torch.empty_like(x)
+    alp_b200.decode(col, out=out)
+    ibits = torch.int64 if vb == 8 else torch.int32
+    verified = bool(torch.equal(out.view(ibits), x.view(ibits)))
+    assert verified, "config %d: decoded column differs from the original" % kind
+    for _ in range(3):
+        alp_b200.decode(col, out=out)
+    dec_ms = cuda_ms(lambda: alp_b200.decode(col, out=out), steps)
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        alp_b200.decode_sum(col, out=acc)
+    scan_ms = cuda_ms(lambda: alp_b200.decode_sum(col, out=acc), steps)
+    acc.zero_()
+    alp_b200.decode_sum(col, out=acc)
+    want = float(x.sum(dtype=torch.float64).item())
+    got = float(acc.item())
+
+    def rate(ms, nbytes):
+        return nbytes / (ms * 1e-3) / 1e9
+
+    block = {
+        "label": label,
+        "values": int(n),
+        "dtype": "f64" if vb == 8 else "f32",
+        "schemes": sorted({2: "ALP", 1: "ALP_RD"}[int(s)] for s in set(meta["scheme"].tolist())),
+        "bits_per_value": 8.0 * read_bytes / n,
+        "exceptions_per_vector": float(meta["exc_cnt"].astype(np.int64).sum()) / max(1, meta.shape[0]),
+        "algorithmic_bytes_per_launch": int(algo),
+        "verified_bit_exact": verified,
+        "decode": {"ms": dec_ms, "GBps": rate(dec_ms, n * vb), "roofline_frac": rate(dec_ms, algo) / peak},
+        "encode": {"ms": t["encode_ms"], "GBps": rate(t["encode_ms"], n * vb), "roofline_frac": rate(t["encode_ms"], algo) / peak, "layout": "vector order"},
+        "encode_unordered": {"ms": t["encode_unordered_ms"], "GBps": rate(t["encode_unordered_ms"], n * vb),
+                             "roofline_frac": rate(t["encode_unordered_ms"], algo) / peak, "layout": "completion order"},
+        "rowgroup_init_ms": t["rowgroup_init_ms"],
+        "init_plus_encode": {"ms": t["init_plus_encode_ms"], "GBps": rate(t["init_plus_encode_ms"], n * vb),
+                             "roofline_frac": rate(t["init_plus_encode_ms"], algo) / peak},
+        "scan_sum": {"ms": scan_ms, "GBps_decoded_equivalent": rate(scan_ms, n * vb), "read_GBps": rate(scan_ms, read_bytes),
+                     "roofline_frac": rate(scan_ms, read_bytes) / peak, "rel_err_vs_torch_sum": abs(got - want) / max(abs(want), 1e-300)},
+    }
+    if cpu_checker is not None:
+        ns = min(n, CPU_SAMPLE_VALUES)
+        block["cpu"] = cpu_legs(cpu_checker, x[:ns].cpu().numpy(), host_threads(), cpu_seconds)
+        c = block["cpu"]
+        block["vs_cpu"] = {
+            "decode": block["decode"]["GBps"] / c["decode_GBps"],
+            "encode": block["encode"]["GBps"] / c["encode_GBps"],
+            "init_plus_encode": block["init_plus_encode"]["GBps"] / c["init_plus_encode_GBps"],
+            "scan_sum": block["scan_sum"]["GBps_decoded_equivalent"] / c["scan_sum_GBps"],
+        }
+    return block, x, col, meta, read_bytes
+
+
+def link_probe(dev, world, barrier, nbytes=1 << 30, reps=3):
+    """Pinned host <-> device copy bandwidth of this rank's PCIe link, measured with every rank copying at the same
+    time (the e2e numbers are bounded by it): each direction alone, then both directions at once on two streams."""
+    import torch
+
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_in.zero_()
+    h_out.zero_()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(h2d, d2h):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_b, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return nbytes * reps / float(t.item()) / 1e9  # per rank, at the pace of the slowest rank
+
+    run(True, True)  # warm-up
+    res = {"h2d_GBps": run(True, False), "d2h_GBps": run(False, True)}
+    both = run(True, True)
+    res["duplex_GBps_each_way"] = both
+    res["ranks_copying_at_once"] = world
+    res["bytes_per_copy"] = nbytes
+    return res
 
 
 def main():
@@ -235,9 +472,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="alp_b200", choices=["alp_b200", "reference"])
     ap.add_argument("--values", type=int, default=int(os.environ.get("ALPB200_BENCH_VALUES", DEFAULT_VALUES)), help="values per GPU")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="budget of the CPU legs, per config")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the config 3 / 4 blocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "alp_b200" else args.warmup
     if args.impl == "reference":
@@ -261,56 +499,34 @@ def main():
     n = (args.values // _abi.VECTOR_SIZE) * _abi.VECTOR_SIZE
     n_vec = n // _abi.VECTOR_SIZE
     launches = 0
+    peak, peak_src = measured_peak()
+    cpu_checker = None
+    if rank == 0 and world == 1:
+        from oracle import pyoracle
+
+        cpu_checker = pyoracle.best()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- untimed set-up: this rank's shard of the global column, compressed on the device ----
-    x = alp_b200.generate(n, KIND, dev, first_index=rank * n)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    big = alp_b200.DeviceColumn(n_vec, 8, dev)  # worst-case capacities; allocated before anything is timed
-    ws = torch.empty(max(256, alp_b200.lib.alpb200_encode_workspace_bytes(n_vec)), dtype=torch.uint8, device=dev)
-    states = alp_b200.rowgroup_init(x)
-    alp_b200.encode(x, states, col=big, workspace=ws)  # warm-up pass (also first touch of the output buffers)
-    alp_b200.encode(x, states, col=big, workspace=ws, ordered=False)
-    torch.cuda.synchronize()
-    ev[3].record()
-    alp_b200.encode(x, states, col=big, workspace=ws, ordered=False)  # completion-order layout (reported beside the default)
-    ev[4].record()
-    del states  # its blocks go back to torch's caching allocator: no cudaMalloc inside the timed init below
-    ev[0].record()
-    states = alp_b200.rowgroup_init(x)
-    ev[1].record()
-    alp_b200.encode(x, states, col=big, workspace=ws)  # the default, vector-order layout: this is the column decoded below
-    ev[2].record()
-    packed_bytes, n_exc = big.read_totals()
-    init_ms, encode_ms, encode_unordered_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[3].elapsed_time(ev[4])
-    # trim the worst-case container to what was used
-    col = alp_b200.DeviceColumn(n_vec, 8, dev, max(packed_bytes, 128), max(n_exc, 1))
-    col.meta.copy_(big.meta)
-    col.packed[:packed_bytes].copy_(big.packed[:packed_bytes])
-    col.exc_val[:n_exc].copy_(big.exc_val[:n_exc])
-    col.exc_pos[:n_exc].copy_(big.exc_pos[:n_exc])
-    col.totals.copy_(big.totals)
-    col.max_block_bytes = big.max_block_bytes
-    del big
-    torch.cuda.empty_cache()
-    meta = col.meta.cpu().numpy().view(_abi.VEC_META_DTYPE).reshape(-1)
-    out = torch.empty(n, dtype=torch.float64, device=dev)
+    # ---- the side configs first (their buffers are gone before the headline column is built) ----
+    configs = {}
+    if not args.no_side:
+        for kind in (3, 4):
+            nk = int(n * SIDE_CONFIGS[kind][2]) // 1024 * 1024
+            block, xk, colk, _, _ = config_block(kind, nk, dev, rank, peak, args.steps, cpu_checker, args.cpu_seconds)
+            configs[str(kind)] = block
+            del xk, colk
+            torch.cuda.empty_cache()
 
-    # correctness of the very thing that is timed: decode == original, bit for bit
-    alp_b200.decode(col, out=out)
-    torch.cuda.synchronize()
-    verified = bool(torch.equal(out.view(torch.int64), x.view(torch.int64)))
-    assert verified, "decoded column differs from the original"
-
-    # algorithmic bytes of one decode launch: 128*bw + 13-byte header + 10 bytes per exception read,
-    # 8192 bytes written, per vector — summed from the column's own metadata
-    hdr = 13
-    read_bytes = int(meta["bw"].astype(np.int64).sum()) * 128 + hdr * n_vec + 10 * int(meta["exc_cnt"].astype(np.int64).sum())
+    # ---- untimed set-up of the headline: this rank's shard of the global column, compressed on the device ----
+    block2, x, col, meta, read_bytes = config_block(KIND, n, dev, rank, peak, args.steps, cpu_checker, args.cpu_seconds)
+    configs[str(KIND)] = block2
+    verified = block2["verified_bit_exact"]
     algo_bytes = read_bytes + n * 8
+    out = torch.empty(n, dtype=torch.float64, device=dev)
 
     # ---- timed region: K decode launches, data resident in HBM (3 GB compressed in, 8 GB out: far beyond L2) ----
     for _ in range(args.warmup):
@@ -333,49 +549,45 @@ def main():
     ms = float(t.item())
     value = world * n * 8.0 / (ms * 1e-3) / 1e9
 
-    # encode side (reported, not the headline): device-timed, input resident
-    enc_gbps = n * 8.0 / (encode_ms * 1e-3) / 1e9
-
-    # fused decode + SUM scan (reported, not the headline): nothing is written back, so the bound is the compressed read
-    acc = torch.zeros(1, dtype=torch.float64, device=dev)
-    for _ in range(3):
-        alp_b200.decode_sum(col, out=acc)
-    torch.cuda.synchronize()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for _ in range(args.steps):
-        alp_b200.decode_sum(col, out=acc)
-    s1.record()
-    torch.cuda.synchronize()
-    scan_ms = s0.elapsed_time(s1) / args.steps
+    def max_over_ranks(seconds):
+        ts = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        return float(ts.item())
 
     # ---- e2e: host column in, host values out, through alpb200_decompress_host ----
     e2e = e2e_scan = e2e_compress = None
     if not args.no_e2e:
+        link = link_probe(dev, world, barrier)
         hcol = pinned_host_column(col.to_host())
         hout_t = torch.empty(n, dtype=torch.float64, pin_memory=True)
         hout = hout_t.numpy()
         codec = alp_b200.HostCodec(n_vec, 8, local)
-        codec.decompress(hcol, out=hout)  # warm-up + check
-        assert hout.view(np.int64)[:: 4099].tobytes() == x.cpu().numpy().view(np.int64)[:: 4099].tobytes()
+        codec.decompress(hcol, out=hout)  # warm-up + check of the whole result (compared on the device)
+        out.copy_(hout_t, non_blocking=True)
+        e2e_ok = bool(torch.equal(out.view(torch.int64), x.view(torch.int64)))
+        assert e2e_ok, "alpb200_decompress_host: result differs from the original"
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             codec.decompress(hcol, out=hout)
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
         h2d = hcol.meta.nbytes + hcol.packed_bytes + hcol.n_exceptions * 10
+        d2h = n * 8
+
         e2e = {
             "value": world * n * 8.0 / e2e_s / 1e9,
             "unit": UNIT,
             "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(n * 8),
+            "d2h_bytes_per_step": int(d2h),
             "ms_per_step": e2e_s * 1e3,
             "steps": args.e2e_steps,
-            "api": "alpb200_decompress_host_f64 (pinned host buffers, 16-chunk pipeline over 3 streams)",
+            "verified_bit_exact": e2e_ok,
+            "api": "alpb200_decompress_host_f64 (pinned host buffers, chunk pipeline over 3 streams)",
+            "link": link,
+            "link_bound_ms": max(h2d / link["h2d_GBps"], d2h / link["d2h_GBps"]) / 1e6,
+            "link_frac": max(h2d / link["h2d_GBps"], d2h / link["d2h_GBps"]) / 1e9 / e2e_s,
+            "bound": "PCIe D2H of the decoded values (8 B/value); link_frac = time the slower copy alone needs at the measured pinned-copy rate / measured time",
         }
         # the scan query end to end: host column in, one double out (only the compressed bytes cross PCIe)
         want_sum = float(x.sum().item())
@@ -385,11 +597,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             codec.sum(hcol)
-        scan_s = (time.perf_counter() - t0) / args.e2e_steps
-        ts = torch.tensor([scan_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        scan_s = float(ts.item())
+        scan_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
         e2e_scan = {
             "value": world * n * 8.0 / scan_s / 1e9,
             "unit": "GB/s of decoded-equivalent f64 scanned",
@@ -397,6 +605,7 @@ def main():
             "d2h_bytes_per_step": 8,
             "ms_per_step": scan_s * 1e3,
             "api": "alpb200_sum_host_f64 (SUM over the host column; reference: bench_end_to_end alp_func + aggr_plus)",
+            "link_frac": h2d / link["h2d_GBps"] / 1e9 / scan_s,
         }
         # the other direction end to end: pinned host values in, pinned host column out (chunk pipeline, H2D-bound)
         ref_packed = hcol.packed[: hcol.packed_bytes].tobytes()
@@ -408,43 +617,48 @@ def main():
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             codec.compress(hout, col=hcol)
-        comp_s = (time.perf_counter() - t0) / args.e2e_steps
-        tc = torch.tensor([comp_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        comp_s = float(tc.item())
+        comp_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
         e2e_compress = {
             "value": world * n * 8.0 / comp_s / 1e9,
             "unit": "GB/s of f64 input compressed",
             "h2d_bytes_per_step": int(n * 8),
             "d2h_bytes_per_step": int(h2d),
             "ms_per_step": comp_s * 1e3,
-            "api": "alpb200_compress_host_f64 (pinned host buffers; row-group init + encode per chunk, 16-chunk pipeline over 3 streams)",
+            "api": "alpb200_compress_host_f64 (pinned host buffers; row-group init + encode per chunk, chunk pipeline over 3 streams)",
+            "link_frac": n * 8 / link["h2d_GBps"] / 1e9 / comp_s,
         }
+        if "cpu" in block2:
+            e2e_scan["cpu_reference_GBps"] = block2["cpu"]["scan_sum_GBps"]
+            e2e_scan["vs_cpu"] = e2e_scan["value"] / block2["cpu"]["scan_sum_GBps"]
+            e2e_compress["cpu_reference_GBps"] = block2["cpu"]["init_plus_encode_GBps"]
+            e2e_compress["vs_cpu"] = e2e_compress["value"] / block2["cpu"]["init_plus_encode_GBps"]
+            e2e["cpu_reference_GBps"] = block2["cpu"]["decode_GBps"]
         codec.close()
+        del hcol, hout, hout_t
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the reference's decode on a bounded slice of this column ----
-    cpu = None
-    if rank == 0 and world == 1:
-        from oracle import pyoracle
+    # ---- N > 1: rank 0 hands ITS compressed column out as row-group shards over NCCL (BASELINE config 5 says
+    # "scattered"); a set-up step, outside the timed decode, reported on its own ----
+    scatter = None
+    if world > 1:
+        from alp_b200 import shard
 
-        checker = pyoracle.best()
-        n_slice_vec = min(n_vec, (1 << 27) // 1024)  # same bounded sample as `--impl reference`
-        sl = col.to_host(0, n_slice_vec)
-        threads = host_threads()
-        gbps, reps, dt = cpu_decode_baseline(sl, threads, args.cpu_seconds, checker)
-        one_gbps, _, _ = cpu_decode_baseline(sl, 1, 1.0, checker)
-        cpu = {
-            "value": gbps,
-            "unit": UNIT,
-            "cores": threads,
-            "kind": checker.kind,
-            "single_thread_value": one_gbps,
-            "sample": "first 2^%d values of the same column decoded %d times in %.1f s (falp + patch_exceptions, %s)" % (int(np.log2(n_slice_vec * 1024)), reps, dt, checker.build_info),
-        }
+        tensors = shard.column_tensors(col) if rank == 0 else None
+        barrier()
+        t0 = time.perf_counter()
+        mine, (first, count) = shard.scatter_column(tensors, src=0, value_bytes=8, device=dev)
+        torch.cuda.synchronize()
+        sc_s = max_over_ranks(time.perf_counter() - t0)
+        shard_col = shard.tensors_to_device_column(mine, 8, dev)
+        got = alp_b200.decode(shard_col)
+        want = alp_b200.generate(count * 1024, KIND, dev, first_index=first * 1024)  # rank 0's column starts at value 0
+        ok = torch.tensor([int(torch.equal(got.view(torch.int64), want.view(torch.int64)))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        sent = read_bytes * (world - 1) / world if rank == 0 else 0
+        scatter = {"ms": sc_s * 1e3, "bytes_sent_by_rank0": int(sent), "GBps": (sent / sc_s / 1e9) if rank == 0 else None,
+                   "shards_decode_bit_exact": bool(ok.item()), "api": "alp_b200.shard.scatter_column (NCCL point-to-point, whole row-groups)"}
+        del shard_col, got, want, mine
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         achieved = algo_bytes / (ms_local * 1e-3) / 1e9
         traffic = None
         try:
@@ -452,6 +666,11 @@ def main():
                 traffic = json.load(fh).get("decode_f64_dram_bytes_per_launch")
         except Exception:
             pass
+        cpu = None
+        if "cpu" in block2:
+            c = block2["cpu"]
+            cpu = {"value": c["decode_GBps"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "single_thread_value": c["decode_single_thread_GBps"],
+                   "sample": c["sample"] + ", decoded %d times (falp + patch_exceptions)" % c["decode_reps"]}
         line = {
             "metric": METRIC,
             "value": value,
@@ -465,15 +684,10 @@ def main():
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD,
-                "values_per_gpu": n,
-                "vectors_per_gpu": n_vec,
-                "bits_per_value": 8.0 * (read_bytes) / n,
-                "l2": "inputs larger than L2 (%.2f GB compressed in, %.2f GB out per step)" % (read_bytes / 1e9, n * 8 / 1e9),
-                "parallelism": "row-group shards, %d rank(s), no data-path collective" % world,
-                "verified_bit_exact": verified,
-            },
+            "config": workload_config(n),
+            "verified_bit_exact": verified,
+            "parallelism": "row-group shards, %d rank(s), no data-path collective" % world,
+            "bits_per_value": 8.0 * read_bytes / n,
             "roofline": {
                 "bound": "hbm",
                 "achieved": achieved,
@@ -491,21 +705,8 @@ def main():
             "clocks": clocks.summary(),
             "e2e_scan": e2e_scan,
             "e2e_compress": e2e_compress,
-            "encode": {
-                "GBps": enc_gbps,
-                "ms": encode_ms,
-                "roofline_frac": algo_bytes / (encode_ms * 1e-3) / 1e9 / peak,
-                "rowgroup_init_ms": init_ms,
-                "bits_per_value": 8.0 * read_bytes / n,
-                "unordered_layout": {"GBps": n * 8.0 / (encode_unordered_ms * 1e-3) / 1e9, "ms": encode_unordered_ms,
-                                     "roofline_frac": algo_bytes / (encode_unordered_ms * 1e-3) / 1e9 / peak},
-            },
-            "scan_sum": {
-                "ms": scan_ms,
-                "GBps_decoded_equivalent": n * 8.0 / (scan_ms * 1e-3) / 1e9,
-                "read_GBps": read_bytes / (scan_ms * 1e-3) / 1e9,
-                "roofline_frac": read_bytes / (scan_ms * 1e-3) / 1e9 / peak,
-            },
+            "configs": configs,
+            "scatter": scatter,
         }
         channel.emit(line)
     if world > 1:

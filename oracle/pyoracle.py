@@ -9,14 +9,30 @@ Two libraries with the same function set (see oracle/alp_oracle.h and oracle/ref
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may import this.
 """
 import ctypes
+import importlib.util
 import os
 import subprocess
+import sys
 
 import numpy as np
 
-from alp_b200 import _abi
-
 _HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load_abi():
+    """The struct declarations of include/alp_b200.h (alp_b200/_abi.py: pure ctypes / numpy images, no library) WITHOUT
+    importing the alp_b200 package, whose __init__ loads the CUDA library: a process that only runs the CPU checker
+    (bench.py --impl reference) must not map the product."""
+    mod = sys.modules.get("alp_b200._abi")
+    if mod is None:
+        spec = importlib.util.spec_from_file_location("alp_b200._abi", os.path.join(os.path.dirname(_HERE), "alp_b200", "_abi.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["alp_b200._abi"] = mod  # a later `import alp_b200` picks up this very module
+        spec.loader.exec_module(mod)
+    return mod
+
+
+_abi = _load_abi()
 _c = ctypes
 _P = ctypes.c_void_p
 
@@ -83,6 +99,10 @@ class CpuCodec:
             f = self._fn("encode_column_" + sfx)
             f.argtypes, f.restype = [_P, _c.c_size_t, _c.c_int, _P], _c.c_int
             f = self._fn("decode_column_" + sfx)
+            f.argtypes, f.restype = [_P, _c.c_size_t, _c.c_size_t, _c.c_int, _P], _c.c_int
+            f = self._fn("bench_encode_" + sfx)
+            f.argtypes, f.restype = [_P, _c.c_size_t, _c.c_int, _P, _P, _c.c_int], _c.c_int
+            f = self._fn("sum_column_" + sfx)
             f.argtypes, f.restype = [_P, _c.c_size_t, _c.c_size_t, _c.c_int, _P], _c.c_int
         self._fn("analyze_ffor_i64").argtypes = [_P, _P, _P]
         self._fn("analyze_ffor_i32").argtypes = [_P, _P, _P]
@@ -218,6 +238,48 @@ class CpuCodec:
         return out
 
 
+    # -- bench drivers (bench.py's CPU legs) ------------------------------------------------------
+    def bench_init(self, values, n_threads=1, states=None):
+        """encoder<PT>::init (+ rd_encoder<PT>::init) for every row-group → RG_STATE array."""
+        values = np.ascontiguousarray(values)
+        sfx = _abi.value_types(values.dtype.itemsize)[3]
+        n_rg = -(-(values.shape[0] // 1024) // _abi.ROWGROUP_VECTORS)
+        if states is None:
+            states = np.zeros(max(n_rg, 1), dtype=_abi.RG_STATE_DTYPE)
+        rc = self._fn("bench_encode_" + sfx)(_ptr(values), values.shape[0], n_threads, None, _ptr(states), 1)
+        if rc != 0:
+            raise RuntimeError("bench_init failed: %d" % rc)
+        return states
+
+    def bench_encode(self, values, n_threads=1, states=None, col=None):
+        """Multi-threaded encode for timing: every thread writes into its own slice of `col` (records carry absolute
+        offsets; slices leave gaps).  states=None runs the row-group init inside the call (init + encode)."""
+        values = np.ascontiguousarray(values)
+        vb = values.dtype.itemsize
+        sfx = _abi.value_types(vb)[3]
+        n_vec = values.shape[0] // 1024
+        if col is None:
+            units = 67 if vb == 8 else 35
+            col = _abi.HostColumn(n_vec, vb, n_vec * units * 128 + n_threads * (units * 128 + 128), n_vec * 1024 + n_threads * 1024)
+        st = col.as_struct()
+        mode = 2 | (1 if states is None else 0)
+        rc = self._fn("bench_encode_" + sfx)(_ptr(values), values.shape[0], n_threads, ctypes.byref(st), None if states is None else _ptr(states), mode)
+        if rc != 0:
+            raise RuntimeError("bench_encode failed: %d" % rc)
+        return col
+
+    def sum_column(self, col, first=0, n=None, n_threads=1):
+        """The reference's scan query: alp_func (falp + patch_exceptions) + aggr_plus per vector, n_threads workers."""
+        sfx = _abi.value_types(col.value_bytes)[3]
+        n = col.n_vectors - first if n is None else n
+        out = ctypes.c_double(0.0)
+        st = col.as_struct()
+        rc = self._fn("sum_column_" + sfx)(ctypes.byref(st), first, n, n_threads, ctypes.byref(out))
+        if rc != 0:
+            raise RuntimeError("sum_column failed: %d" % rc)
+        return float(out.value)
+
+
 _PORT = None
 _REF = "unset"
 
@@ -257,15 +319,25 @@ def best():
     return reference() or port()
 
 
-def generate(n_values, kind, seed=None, first_index=0):
-    """CPU twin of alpb200_generate_* (SURVEY.md §8d): kind 2/3 → f64, kind 4 → f32."""
+def generate(n_values, kind, seed=None, first_index=0, n_threads=1):
+    """CPU twin of alpb200_generate_* (SURVEY.md §8d): kind 2/3 → f64, kind 4 → f32.  The generator is stateless per
+    index, so n_threads > 1 simply fills disjoint slices concurrently (ctypes releases the GIL)."""
     seeds = {2: 42, 3: 43, 4: 44}
     seed = seeds[kind] if seed is None else seed
     lib = port().lib
-    if kind == 4:
-        out = np.empty(n_values, dtype=np.float32)
-        lib.alpo_generate_f32(_ptr(out), n_values, first_index, seed, kind)
+    out = np.empty(n_values, dtype=np.float32 if kind == 4 else np.float64)
+    fn = lib.alpo_generate_f32 if kind == 4 else lib.alpo_generate_f64
+
+    def fill(lo, hi):
+        if hi > lo:
+            fn(_ptr(out[lo:hi]), hi - lo, first_index + lo, seed, kind)
+
+    if n_threads <= 1 or n_values < (1 << 20):
+        fill(0, n_values)
     else:
-        out = np.empty(n_values, dtype=np.float64)
-        lib.alpo_generate_f64(_ptr(out), n_values, first_index, seed, kind)
+        from concurrent.futures import ThreadPoolExecutor
+
+        step = -(-n_values // n_threads)
+        with ThreadPoolExecutor(max_workers=n_threads) as pool:
+            list(pool.map(lambda k: fill(k * step, min(n_values, (k + 1) * step)), range(n_threads)))
     return out

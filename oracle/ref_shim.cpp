@@ -272,6 +272,168 @@ int ref_decode_column(const alpb200_column* col, size_t first, size_t n, int n_t
 	return ALPB200_OK;
 }
 
+
+/* ---- bench drivers (bench.py's CPU legs): the same call sequences, laid out for throughput ------------------------
+ * Row-groups are dealt to the threads as contiguous ranges and every thread writes its blocks / exceptions into its own
+ * slice of the container (slice k of n_threads of the packed and exception arrays), so there is no serial pass and no
+ * per-vector allocation inside the timed region.  The result is a valid column container (records carry absolute
+ * offsets; the slices leave gaps between them), which the caller decodes to check the timed run.
+ * mode bit 0: run alp::encoder<PT>::init (+ rd_encoder<PT>::init) per row-group — test/test_alp_sample.cpp:137-141 —
+ *             otherwise take the states from `states`;  bit 1: encode the vectors — :143-145 / :164-166
+ *             (encode + analyze_ffor + ffor, or rd encode + 2x ffor); without it only the states are produced. */
+template <typename PT>
+int ref_bench_encode(const PT* col, size_t n_values, int n_threads, alpb200_column* out, alpb200_rg_state* states, int mode) {
+	using UT = typename alp::inner_t<PT>::ut;
+	using ST = typename alp::inner_t<PT>::st;
+	const size_t n_vec = n_values / alp::config::VECTOR_SIZE;
+	const size_t n_rg  = (n_vec + alp::config::N_VECTORS_PER_ROWGROUP - 1) / alp::config::N_VECTORS_PER_ROWGROUP;
+	n_values           = n_vec * alp::config::VECTOR_SIZE;
+	if (n_threads < 1) { n_threads = 1; }
+	const bool do_init = (mode & 1) != 0, do_encode = (mode & 2) != 0;
+	if ((!do_init && !states) || (do_encode && !out)) { return ALPB200_EINVAL; }
+	std::atomic<int>      overflow {0};
+	std::vector<uint64_t> used_p(n_threads, 0), used_e(n_threads, 0);
+	auto                  work = [&](int k) {
+        const size_t rg0 = n_rg * k / n_threads, rg1 = n_rg * (k + 1) / n_threads;
+        uint64_t     p_lo = 0, p_hi = 0, e_lo = 0, e_hi = 0;
+        if (do_encode) {
+            p_lo = (out->packed_capacity / n_threads * k) & ~uint64_t(127);
+            p_hi = (out->packed_capacity / n_threads * (k + 1)) & ~uint64_t(127);
+            e_lo = out->exc_capacity / n_threads * k;
+            e_hi = out->exc_capacity / n_threads * (k + 1);
+        }
+        uint64_t        poff = p_lo, eoff = e_lo;
+        std::vector<PT> sample(alp::config::VECTOR_SIZE);
+        alignas(64) PT       exc[1024];
+        alignas(64) uint16_t rdexc[1024], pos[1024], cnt[8], left[1024];
+        alignas(64) ST       enc[1024], base[8];
+        alignas(64) UT       right[1024];
+        for (size_t rg = rg0; rg < rg1; rg++) {
+            const size_t   first = rg * alp::config::ROWGROUP_SIZE;
+            const size_t   nv    = std::min(n_values - first, alp::config::ROWGROUP_SIZE) / alp::config::VECTOR_SIZE;
+            alp::state<PT> stt;
+            if (do_init) {
+                alp::encoder<PT>::init(col, first, n_values, sample.data(), stt);
+                if (stt.scheme == alp::Scheme::ALP_RD) { alp::rd_encoder<PT>::init(col, first, n_values, sample.data(), stt); }
+                if (states) { from_ref_state(stt, &states[rg]); }
+            } else {
+                to_ref_state(&states[rg], stt);
+            }
+            if (!do_encode) { continue; }
+            const bool rd = stt.scheme == alp::Scheme::ALP_RD;
+            for (size_t v = 0; v < nv; v++) {
+                const PT*         in = col + first + v * alp::config::VECTOR_SIZE;
+                alpb200_vec_meta& m  = out->meta[rg * alp::config::N_VECTORS_PER_ROWGROUP + v];
+                std::memset(&m, 0, sizeof(m));
+                const uint64_t worst = 128u * (sizeof(PT) * 8 + 3);
+                if (poff + worst > p_hi || eoff + 1024 > e_hi) {
+                    overflow = 1;
+                    return;
+                }
+                uint8_t* dst = out->packed + poff;
+                if (rd) {
+                    alp::rd_encoder<PT>::encode(in, rdexc, pos, cnt, right, left, stt);
+                    ffor::ffor(right, reinterpret_cast<UT*>(dst), stt.right_bit_width, &stt.right_for_base);
+                    ffor::ffor(left, reinterpret_cast<uint16_t*>(dst + 128u * stt.right_bit_width), stt.left_bit_width, &stt.left_for_base);
+                    m.scheme = ALPB200_SCHEME_ALP_RD;
+                    m.bw     = stt.right_bit_width;
+                    m.e      = stt.left_bit_width;
+                    m.f      = stt.actual_dictionary_size;
+                    for (int i = 0; i < ALPB200_RD_DICT_SIZE; i++) {
+                        m.u.rd_dict[i] = stt.left_parts_dict[i];
+                    }
+                    UT* ev = static_cast<UT*>(out->exc_val) + eoff;
+                    for (int i = 0; i < cnt[0]; i++) {
+                        ev[i] = rdexc[i];
+                    }
+                    m.packed_off = static_cast<uint32_t>(poff / 128);
+                    poff += 128u * (stt.right_bit_width + stt.left_bit_width);
+                } else {
+                    uint8_t bw = 0;
+                    alp::encoder<PT>::encode(in, exc, pos, cnt, enc, stt);
+                    alp::encoder<PT>::analyze_ffor(enc, bw, base);
+                    ffor::ffor(enc, reinterpret_cast<ST*>(dst), bw, base);
+                    m.scheme     = ALPB200_SCHEME_ALP;
+                    m.bw         = bw;
+                    m.e          = stt.exp;
+                    m.f          = stt.fac;
+                    m.u.alp.base = static_cast<int64_t>(base[0]);
+                    std::memcpy(static_cast<PT*>(out->exc_val) + eoff, exc, cnt[0] * sizeof(PT));
+                    m.packed_off = static_cast<uint32_t>(poff / 128);
+                    poff += 128u * bw;
+                }
+                std::memcpy(out->exc_pos + eoff, pos, cnt[0] * sizeof(uint16_t));
+                m.exc_off = static_cast<uint32_t>(eoff);
+                m.exc_cnt = cnt[0];
+                eoff += cnt[0];
+            }
+        }
+        used_p[k] = poff - p_lo;
+        used_e[k] = eoff - e_lo;
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < n_threads; t++) {
+		pool.emplace_back(work, t);
+	}
+	work(0);
+	for (auto& t : pool) {
+		t.join();
+	}
+	if (do_encode) {
+		out->n_vectors = n_vec;
+		if (out->totals) {  // bytes / slots actually written (the container's slices are not dense)
+			uint64_t p = 0, e = 0;
+			for (int k = 0; k < n_threads; k++) {
+				p += used_p[k];
+				e += used_e[k];
+			}
+			out->totals[0] = p;
+			out->totals[1] = e;
+			out->totals[2] = overflow.load();
+		}
+	}
+	return overflow.load() ? ALPB200_ECAPACITY : ALPB200_OK;
+}
+
+/* The reference's scan query: per vector the scan primitive `alp_func` (fused falp + patch_exceptions into a
+ * thread-private 1024-value buffer, publication/source_code/bench_end_to_end/src/benchmarks/alp/queries/q1.cpp:63-89)
+ * followed by `aggr_plus` (out[0] += in[i], q1.cpp:91-100), on n_threads workers over disjoint morsels of vectors
+ * (TBB workers in the reference, q1.cpp:650-679); the workers' aggregates are added at the end. */
+template <typename PT>
+int ref_sum_column(const alpb200_column* col, size_t first, size_t n, int n_threads, double* out) {
+	if (n_threads < 1) { n_threads = 1; }
+	std::atomic<size_t> next {0};
+	const size_t        chunk = 64;
+	std::vector<double> partial(n_threads, 0.0);
+	auto                work = [&](int k) {
+        alignas(64) PT buf[1024];
+        double         aggr = 0.0;
+        for (size_t c = next.fetch_add(chunk); c < n; c = next.fetch_add(chunk)) {
+            for (size_t v = c; v < std::min(n, c + chunk); v++) {
+                decode_vector<PT>(col, first + v, buf);
+                for (size_t i = 0; i < 1024; ++i) {
+                    aggr += buf[i];
+                }
+            }
+        }
+        partial[k] = aggr;
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < n_threads; t++) {
+		pool.emplace_back(work, t);
+	}
+	work(0);
+	for (auto& t : pool) {
+		t.join();
+	}
+	double total = 0.0;
+	for (double p : partial) {
+		total += p;
+	}
+	*out = total;
+	return ALPB200_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -388,5 +550,20 @@ int alpref_decode_column_f64(const alpb200_column* col, size_t first, size_t n, 
 int alpref_decode_column_f32(const alpb200_column* col, size_t first, size_t n, int n_threads, float* out) {
 	return ref_decode_column<float>(col, first, n, n_threads, out);
 }
+
+/* bench drivers (see ref_bench_encode / ref_sum_column above) */
+int alpref_bench_encode_f64(const double* col, size_t n_values, int n_threads, alpb200_column* out, alpb200_rg_state* states, int mode) {
+	return ref_bench_encode<double>(col, n_values, n_threads, out, states, mode);
+}
+int alpref_bench_encode_f32(const float* col, size_t n_values, int n_threads, alpb200_column* out, alpb200_rg_state* states, int mode) {
+	return ref_bench_encode<float>(col, n_values, n_threads, out, states, mode);
+}
+int alpref_sum_column_f64(const alpb200_column* col, size_t first, size_t n, int n_threads, double* out) {
+	return ref_sum_column<double>(col, first, n, n_threads, out);
+}
+int alpref_sum_column_f32(const alpb200_column* col, size_t first, size_t n, int n_threads, double* out) {
+	return ref_sum_column<float>(col, first, n, n_threads, out);
+}
+
 
 } // extern "C"
