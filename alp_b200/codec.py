@@ -225,14 +225,19 @@ class HostCodec:
     """alpb200_ctx: compress / decompress columns that live in HOST memory (copies are part of each call)."""
 
     OPT_UNORDERED = 1  # ALPB200_OPT_UNORDERED
+    OPT_CHUNKS = 2  # ALPB200_OPT_CHUNKS
 
-    def __init__(self, max_vectors, value_bytes=8, device=0, ordered=True):
+    def __init__(self, max_vectors, value_bytes=8, device=0, ordered=True, packed_capacity=0, exc_capacity=0, chunks=None):
+        """packed_capacity / exc_capacity: the caller's bound on the compressed column (bytes / exception slots) the device
+        staging is sized for; 0 = the worst case any column can reach (~27 bytes per f64 value)."""
         self.value_bytes = value_bytes
         self.max_vectors = int(max_vectors)
         self._ctx = ctypes.c_void_p()
-        check(lib.alpb200_ctx_create(ctypes.byref(self._ctx), device, self.max_vectors, value_bytes))
+        check(lib.alpb200_ctx_create_ex(ctypes.byref(self._ctx), device, self.max_vectors, value_bytes, int(packed_capacity), int(exc_capacity)))
         if not ordered:
             check(lib.alpb200_ctx_set_option(self._ctx, self.OPT_UNORDERED, 1))
+        if chunks is not None:
+            check(lib.alpb200_ctx_set_option(self._ctx, self.OPT_CHUNKS, int(chunks)))
 
     def close(self):
         if self._ctx:
@@ -245,8 +250,16 @@ class HostCodec:
         except Exception:
             pass
 
+    def _check_values(self, arr, what, n_min=0):
+        want = _abi.value_types(self.value_bytes)[0]
+        if not isinstance(arr, np.ndarray) or arr.dtype != want or arr.ndim != 1 or not arr.flags["C_CONTIGUOUS"]:
+            raise ValueError("%s must be a contiguous 1-D numpy array of %s" % (what, want))
+        if arr.shape[0] < n_min:
+            raise ValueError("%s holds %d values, %d are needed" % (what, arr.shape[0], n_min))
+
     def compress(self, values, col=None):
         values = np.ascontiguousarray(values)
+        self._check_values(values, "values")
         n_vec = -(-values.shape[0] // _abi.VECTOR_SIZE)  # a partial last vector is padded by the library
         if col is None:
             col = _abi.HostColumn(n_vec, self.value_bytes)
@@ -265,9 +278,18 @@ class HostCodec:
         check(fn(self._ctx, ctypes.byref(st), ctypes.byref(out)))
         return float(out.value)
 
+    def validate(self, col):
+        """alpb200_column_validate_host: raises AlpError(EINVAL) for a malformed host column."""
+        st = col.as_struct()
+        check(lib.alpb200_column_validate_host(ctypes.byref(st), self.value_bytes))
+
     def decompress(self, col, out=None):
+        n_out = col.n_values or col.n_vectors * _abi.VECTOR_SIZE
+        if col.value_bytes != self.value_bytes:
+            raise ValueError("the column holds %d-byte values, the codec was created for %d" % (col.value_bytes, self.value_bytes))
         if out is None:
-            out = np.empty(col.n_values or col.n_vectors * _abi.VECTOR_SIZE, dtype=_abi.value_types(self.value_bytes)[0])
+            out = np.empty(n_out, dtype=_abi.value_types(self.value_bytes)[0])
+        self._check_values(out, "out", n_out)
         st = col.as_struct()
         fn = getattr(lib, "alpb200_decompress_host_" + _sfx(self.value_bytes))
         check(fn(self._ctx, ctypes.byref(st), out.ctypes.data))

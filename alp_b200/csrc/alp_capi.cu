@@ -87,13 +87,27 @@ struct alpb200_ctx {
 	cudaEvent_t       chunk_in[MAX_CHUNKS]  = {};
 	cudaEvent_t       chunk_enc[MAX_CHUNKS] = {};
 	bool              unordered = false;   // ALPB200_OPT_UNORDERED: compress_host encodes with the completion-order layout
+	uint64_t          chunks    = MAX_CHUNKS;  // ALPB200_OPT_CHUNKS: pipeline depth of the host entry points (1..16)
 };
 
 namespace {
 
+// keeps the caller's current device across a host entry point
+struct DeviceGuard {
+	int  prev = -1;
+	bool ok   = false;
+	explicit DeviceGuard(int dev) {
+		ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess;
+		if (!ok) { cudaGetLastError(); }
+	}
+	~DeviceGuard() {
+		if (prev >= 0) { cudaSetDevice(prev); }
+	}
+};
+
 void ctx_release(alpb200_ctx* c) {
 	if (!c) { return; }
-	cudaSetDevice(c->device);
+	DeviceGuard guard(c->device);
 	for (int i = 0; i < 3; i++) {
 		if (c->streams[i]) { cudaStreamDestroy(c->streams[i]); }
 		if (c->events[i]) { cudaEventDestroy(c->events[i]); }
@@ -129,7 +143,8 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_
 	const uint64_t n_vec    = (n_values_in + VEC - 1) / VEC;
 	const uint64_t n_values = n_vec * VEC;  // padded length
 	if (n_vec > c->max_vectors || n_vec > h_col->n_vectors) { return fail(ALPB200_EINVAL, "compress_host: column larger than the context / container"); }
-	CUDA_TRY(cudaSetDevice(c->device));
+	DeviceGuard guard(c->device);
+	if (!guard.ok) { return fail(ALPB200_ECUDA, "compress_host: cannot select the context's device"); }
 	if (n_vec == 0) {
 		h_col->n_vectors = 0;
 		h_col->n_values  = 0;
@@ -138,7 +153,7 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_
 	}
 	cudaStream_t   s_in = c->streams[0], s_enc = c->streams[1], s_out = c->streams[2];
 	const uint64_t n_rg      = (n_vec + ALPB200_ROWGROUP_VECTORS - 1) / ALPB200_ROWGROUP_VECTORS;
-	const uint64_t chunk_rg  = std::max<uint64_t>(10, (n_rg + MAX_CHUNKS - 1) / MAX_CHUNKS);  // at least ~8 MiB of f64 per chunk
+	const uint64_t chunk_rg  = std::max<uint64_t>(10, (n_rg + c->chunks - 1) / c->chunks);  // at least ~8 MiB of f64 per chunk
 	const uint64_t chunk_vec = chunk_rg * ALPB200_ROWGROUP_VECTORS;
 	const int      n_chunks  = (int)((n_vec + chunk_vec - 1) / chunk_vec);
 	PT*            d_values  = static_cast<PT*>(c->d_values);
@@ -211,20 +226,53 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_
 // twice).
 struct ChunkRange {
 	uint64_t p0, p1, e0, e1;
+	uint32_t widest;  // largest packed block of the range, bytes
+	bool     valid;
 };
 inline uint64_t block_units(const alpb200_vec_meta& m) { return m.scheme == ALPB200_SCHEME_ALP_RD ? (uint64_t)m.bw + m.e : m.bw; }
-ChunkRange chunk_range(const alpb200_vec_meta* hm, uint64_t v0, uint64_t v1) {
-	ChunkRange r {UINT64_MAX, 0, UINT64_MAX, 0};
+// what a well-formed record can say (the encoders never write anything else)
+inline bool record_ok(const alpb200_vec_meta& m, int value_bytes) {
+	const uint32_t T = 8u * (uint32_t)value_bytes, max_exp = value_bytes == 8 ? 18u : 10u;
+	if (m.exc_cnt > VEC) { return false; }
+	if (m.scheme == ALPB200_SCHEME_ALP) { return m.bw <= T && m.e <= max_exp && m.f <= m.e; }
+	if (m.scheme == ALPB200_SCHEME_ALP_RD) { return m.bw < T && m.bw + 16u >= T && m.e >= 1 && m.e <= 3 && m.f >= 1 && m.f <= ALPB200_RD_DICT_SIZE; }
+	return false;
+}
+// Walks the records of [v0, v1): byte / slot ranges, the widest block, and whether every record is well formed.  With
+// host_col the exception positions are checked too (each must lie inside the vector).
+ChunkRange chunk_range(const alpb200_vec_meta* hm, uint64_t v0, uint64_t v1, int value_bytes, const alpb200_column* host_col = nullptr) {
+	ChunkRange r {UINT64_MAX, 0, UINT64_MAX, 0, 0, true};
 	for (uint64_t v = v0; v < v1; v++) {
 		const alpb200_vec_meta& m = hm[v];
-		const uint64_t          p = (uint64_t)m.packed_off * 128ull, e = m.exc_off;
+		if (!record_ok(m, value_bytes)) {
+			r.valid = false;
+			continue;
+		}
+		const uint64_t p = (uint64_t)m.packed_off * 128ull, e = m.exc_off;
 		r.p0 = std::min(r.p0, p);
 		r.p1 = std::max<uint64_t>(r.p1, p + block_units(m) * 128ull);
 		r.e0 = std::min(r.e0, e);
 		r.e1 = std::max<uint64_t>(r.e1, e + m.exc_cnt);
+		r.widest = std::max<uint32_t>(r.widest, (uint32_t)(block_units(m) * 128ull));
+		if (host_col && host_col->exc_pos && e + m.exc_cnt <= host_col->exc_capacity) {
+			const uint16_t* ep = host_col->exc_pos + e;
+			uint32_t        bad = 0;
+			for (uint32_t i = 0; i < m.exc_cnt; i++) {
+				bad |= ep[i] >= VEC;
+			}
+			if (bad) { r.valid = false; }
+		}
 	}
-	if (v0 >= v1) { r = ChunkRange {0, 0, 0, 0}; }
+	if (v0 >= v1 || r.p0 == UINT64_MAX) { r.p0 = r.p1 = r.e0 = r.e1 = 0; }
 	return r;
+}
+// the host column's own arrays must cover what its records point at
+int check_host_column(const alpb200_column* h_col, const ChunkRange& cr, const char* who) {
+	if (!cr.valid) { return fail(ALPB200_EINVAL, "%s: malformed vector record (scheme / bit width / exponent / exception count or position out of range)", who); }
+	if (cr.p1 > h_col->packed_capacity || cr.e1 > h_col->exc_capacity) {
+		return fail(ALPB200_EINVAL, "%s: a vector record points outside the column's packed / exception arrays", who);
+	}
+	return ALPB200_OK;
 }
 // Chunked pipeline: while chunk i decodes and drains to the host on one stream, chunk i+1's compressed bytes are
 // already travelling on another (PCIe is full duplex).  Chunks are whole ranges of vectors; thanks to the vector-order
@@ -236,47 +284,50 @@ int decompress_host(alpb200_ctx* c, const alpb200_column* h_col, PT* h_out) {
 	const uint64_t n_vec = h_col->n_vectors;
 	if (n_vec > c->max_vectors) { return fail(ALPB200_EINVAL, "decompress_host: column larger than the context"); }
 	if (n_vec == 0) { return ALPB200_OK; }
+	if (!h_col->packed || !h_col->exc_val || !h_col->exc_pos) { return fail(ALPB200_EINVAL, "decompress_host: null argument"); }
 	const uint64_t n_out = h_col->n_values ? h_col->n_values : n_vec * VEC;  // a padded tail is not returned
 	if (n_out > n_vec * VEC || n_out + VEC <= n_vec * VEC) { return fail(ALPB200_EINVAL, "decompress_host: n_values does not match n_vectors"); }
-	CUDA_TRY(cudaSetDevice(c->device));
+	DeviceGuard guard(c->device);
+	if (!guard.ok) { return fail(ALPB200_ECUDA, "decompress_host: cannot select the context's device"); }
 	const alpb200_vec_meta* hm = h_col->meta;
 	alpb200_column d_col {};
 	d_col.n_vectors       = n_vec;
 	d_col.meta            = c->d_meta;
 	d_col.packed          = c->d_packed;
+	d_col.packed_capacity = c->packed_capacity;
 	d_col.exc_val         = c->d_exc_val;
 	d_col.exc_pos         = c->d_exc_pos;
-	d_col.max_block_bytes = h_col->max_block_bytes;
+	d_col.exc_capacity    = c->exc_capacity;
 
-	const uint64_t chunk = std::max<uint64_t>(1024, (n_vec + 15) / 16);  // ~16 chunks, at least 8 MiB of f64 output each
-	int            si    = 0;
-	for (uint64_t v0 = 0; v0 < n_vec; v0 += chunk, si = (si + 1) % 3) {
-		const uint64_t   v1 = std::min(n_vec, v0 + chunk);
-		cudaStream_t     s  = c->streams[si];
-		const ChunkRange cr = chunk_range(hm, v0, v1);  // scanned chunk by chunk: the first copy starts at once
-		if (cr.p1 > c->packed_capacity || cr.e1 > c->exc_capacity) {
-			for (int i = 0; i < 3; i++) {
-				cudaStreamSynchronize(c->streams[i]);
-			}
-			return fail(ALPB200_ECAPACITY, "decompress_host: column exceeds the context's staging capacity");
-		}
-		const uint64_t p0 = cr.p0, p1 = cr.p1, e0 = cr.e0, e1 = cr.e1;
-		CUDA_TRY(cudaMemcpyAsync(c->d_meta + v0, hm + v0, (v1 - v0) * sizeof(alpb200_vec_meta), cudaMemcpyHostToDevice, s));
-		if (p1 > p0) { CUDA_TRY(cudaMemcpyAsync(c->d_packed + p0, h_col->packed + p0, p1 - p0, cudaMemcpyHostToDevice, s)); }
-		if (e1 > e0) {
-			CUDA_TRY(cudaMemcpyAsync(static_cast<PT*>(c->d_exc_val) + e0, static_cast<const PT*>(h_col->exc_val) + e0, (e1 - e0) * sizeof(PT),
-			                         cudaMemcpyHostToDevice, s));
-			CUDA_TRY(cudaMemcpyAsync(c->d_exc_pos + e0, h_col->exc_pos + e0, (e1 - e0) * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
-		}
-		PT* d_out = static_cast<PT*>(c->d_values) + v0 * VEC;
-		TRY(launch_decode<PT>(&d_col, v0, v1 - v0, d_out, s));
-		const uint64_t n_copy = std::min<uint64_t>((v1 - v0) * VEC, n_out - v0 * VEC);
-		CUDA_TRY(cudaMemcpyAsync(h_out + v0 * VEC, d_out, n_copy * sizeof(PT), cudaMemcpyDeviceToHost, s));
+	const uint64_t chunk = std::max<uint64_t>(1024, (n_vec + c->chunks - 1) / c->chunks);  // ~16 chunks, at least 8 MiB of f64 output each
+	int            si = 0, rc = ALPB200_OK;
+	auto           body = [&](uint64_t v0, uint64_t v1, cudaStream_t s) -> int {
+        const ChunkRange cr = chunk_range(hm, v0, v1, sizeof(PT), h_col);  // scanned chunk by chunk: the first copy starts at once
+        TRY(check_host_column(h_col, cr, "decompress_host"));
+        if (cr.p1 > c->packed_capacity || cr.e1 > c->exc_capacity) { return fail(ALPB200_ECAPACITY, "decompress_host: column exceeds the context's staging capacity"); }
+        const uint64_t p0 = cr.p0, p1 = cr.p1, e0 = cr.e0, e1 = cr.e1;
+        CUDA_TRY(cudaMemcpyAsync(c->d_meta + v0, hm + v0, (v1 - v0) * sizeof(alpb200_vec_meta), cudaMemcpyHostToDevice, s));
+        if (p1 > p0) { CUDA_TRY(cudaMemcpyAsync(c->d_packed + p0, h_col->packed + p0, p1 - p0, cudaMemcpyHostToDevice, s)); }
+        if (e1 > e0) {
+            CUDA_TRY(cudaMemcpyAsync(static_cast<PT*>(c->d_exc_val) + e0, static_cast<const PT*>(h_col->exc_val) + e0, (e1 - e0) * sizeof(PT),
+                                     cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_exc_pos + e0, h_col->exc_pos + e0, (e1 - e0) * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        }
+        PT* d_out            = static_cast<PT*>(c->d_values) + v0 * VEC;
+        d_col.max_block_bytes = cr.widest;  // the chunk's true widest block, never the caller's hint
+        TRY(launch_decode<PT>(&d_col, v0, v1 - v0, d_out, s));
+        const uint64_t n_copy = std::min<uint64_t>((v1 - v0) * VEC, n_out - v0 * VEC);
+        CUDA_TRY(cudaMemcpyAsync(h_out + v0 * VEC, d_out, n_copy * sizeof(PT), cudaMemcpyDeviceToHost, s));
+        return ALPB200_OK;
+	};
+	for (uint64_t v0 = 0; v0 < n_vec && rc == ALPB200_OK; v0 += chunk, si = (si + 1) % 3) {
+		rc = body(v0, std::min(n_vec, v0 + chunk), c->streams[si]);
 	}
-	for (int i = 0; i < 3; i++) {
-		CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
+	for (int i = 0; i < 3; i++) {  // also on failure: nothing may still be running on the caller's buffers
+		cudaError_t err = cudaStreamSynchronize(c->streams[i]);
+		if (err != cudaSuccess && rc == ALPB200_OK) { rc = fail(ALPB200_ECUDA, "decompress_host: %s", cudaGetErrorString(err)); }
 	}
-	return ALPB200_OK;
+	return rc;
 }
 
 // SUM of a host column: the chunk pipeline of decompress_host with the fused decode+SUM kernel and no values coming
@@ -289,38 +340,39 @@ int sum_host(alpb200_ctx* c, const alpb200_column* h_col, double* h_sum) {
 	if (n_vec > c->max_vectors) { return fail(ALPB200_EINVAL, "sum_host: column larger than the context"); }
 	*h_sum = 0.0;
 	if (n_vec == 0) { return ALPB200_OK; }
+	if (!h_col->packed || !h_col->exc_val || !h_col->exc_pos) { return fail(ALPB200_EINVAL, "sum_host: null argument"); }
 	const uint64_t n_out = h_col->n_values ? h_col->n_values : n_vec * VEC;
 	if (n_out > n_vec * VEC || n_out + VEC <= n_vec * VEC) { return fail(ALPB200_EINVAL, "sum_host: n_values does not match n_vectors"); }
-	CUDA_TRY(cudaSetDevice(c->device));
+	DeviceGuard guard(c->device);
+	if (!guard.ok) { return fail(ALPB200_ECUDA, "sum_host: cannot select the context's device"); }
 	const alpb200_vec_meta* hm = h_col->meta;
 	alpb200_column d_col {};
 	d_col.n_vectors       = n_vec;
 	d_col.meta            = c->d_meta;
 	d_col.packed          = c->d_packed;
+	d_col.packed_capacity = c->packed_capacity;
 	d_col.exc_val         = c->d_exc_val;
 	d_col.exc_pos         = c->d_exc_pos;
-	d_col.max_block_bytes = h_col->max_block_bytes;
+	d_col.exc_capacity    = c->exc_capacity;
 	double* d_sum         = reinterpret_cast<double*>(c->d_totals);  // 32 bytes of device scratch owned by the context
-	CUDA_TRY(cudaMemsetAsync(d_sum, 0, sizeof(double), c->streams[0]));
-	CUDA_TRY(cudaEventRecord(c->events[0], c->streams[0]));
-	for (int i = 1; i < 3; i++) {
-		CUDA_TRY(cudaStreamWaitEvent(c->streams[i], c->events[0], 0));
-	}
 	// a padded tail vector is summed on its own so that the padding can be taken out again (it repeats the last value)
 	const bool     ragged = n_out != n_vec * VEC;
 	const uint64_t n_full = ragged ? n_vec - 1 : n_vec;
-	const uint64_t chunk = std::max<uint64_t>(1024, (n_vec + 15) / 16);  // ~16 chunks, at least 8 MiB of f64 output each
-	int            si    = 0;
-	for (uint64_t v0 = 0; v0 < n_vec; v0 += chunk, si = (si + 1) % 3) {
-		const uint64_t   v1 = std::min(n_vec, v0 + chunk);
-		cudaStream_t     s  = c->streams[si];
-		const ChunkRange cr = chunk_range(hm, v0, v1);  // scanned chunk by chunk: the first copy starts at once
-		if (cr.p1 > c->packed_capacity || cr.e1 > c->exc_capacity) {
-			for (int i = 0; i < 3; i++) {
-				cudaStreamSynchronize(c->streams[i]);
-			}
-			return fail(ALPB200_ECAPACITY, "sum_host: column exceeds the context's staging capacity");
-		}
+	const uint64_t chunk  = std::max<uint64_t>(1024, (n_vec + c->chunks - 1) / c->chunks);
+	int            si = 0, rc = ALPB200_OK;
+	uint32_t       tail_widest = 0;
+	auto           prologue = [&]() -> int {
+        CUDA_TRY(cudaMemsetAsync(d_sum, 0, sizeof(double), c->streams[0]));
+        CUDA_TRY(cudaEventRecord(c->events[0], c->streams[0]));
+        for (int i = 1; i < 3; i++) {
+            CUDA_TRY(cudaStreamWaitEvent(c->streams[i], c->events[0], 0));
+        }
+        return ALPB200_OK;
+	};
+	auto body = [&](uint64_t v0, uint64_t v1, cudaStream_t s) -> int {
+		const ChunkRange cr = chunk_range(hm, v0, v1, sizeof(PT), h_col);
+		TRY(check_host_column(h_col, cr, "sum_host"));
+		if (cr.p1 > c->packed_capacity || cr.e1 > c->exc_capacity) { return fail(ALPB200_ECAPACITY, "sum_host: column exceeds the context's staging capacity"); }
 		const uint64_t p0 = cr.p0, p1 = cr.p1, e0 = cr.e0, e1 = cr.e1;
 		CUDA_TRY(cudaMemcpyAsync(c->d_meta + v0, hm + v0, (v1 - v0) * sizeof(alpb200_vec_meta), cudaMemcpyHostToDevice, s));
 		if (p1 > p0) { CUDA_TRY(cudaMemcpyAsync(c->d_packed + p0, h_col->packed + p0, p1 - p0, cudaMemcpyHostToDevice, s)); }
@@ -329,16 +381,26 @@ int sum_host(alpb200_ctx* c, const alpb200_column* h_col, double* h_sum) {
 			                         cudaMemcpyHostToDevice, s));
 			CUDA_TRY(cudaMemcpyAsync(c->d_exc_pos + e0, h_col->exc_pos + e0, (e1 - e0) * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
 		}
-		const uint64_t stop = std::min(v1, n_full);
+		const uint64_t stop   = std::min(v1, n_full);
+		d_col.max_block_bytes = cr.widest;
+		tail_widest           = cr.widest;
 		if (stop > v0) { TRY(launch_decode_sum<PT>(&d_col, v0, stop - v0, d_sum, s)); }
+		return ALPB200_OK;
+	};
+	rc = prologue();
+	for (uint64_t v0 = 0; v0 < n_vec && rc == ALPB200_OK; v0 += chunk, si = (si + 1) % 3) {
+		rc = body(v0, std::min(n_vec, v0 + chunk), c->streams[si]);
 	}
-	for (int i = 0; i < 3; i++) {
-		CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
+	for (int i = 0; i < 3; i++) {  // also on failure: nothing may still be reading the caller's column
+		cudaError_t err = cudaStreamSynchronize(c->streams[i]);
+		if (err != cudaSuccess && rc == ALPB200_OK) { rc = fail(ALPB200_ECUDA, "sum_host: %s", cudaGetErrorString(err)); }
 	}
+	if (rc != ALPB200_OK) { return rc; }
 	double total = 0.0;
 	if (ragged) {  // decode the last vector (4-8 KiB) and add its real values on the host
 		cudaStream_t s = c->streams[0];
 		PT*          d_tail = static_cast<PT*>(c->d_values);
+		d_col.max_block_bytes = tail_widest;
 		TRY(launch_decode<PT>(&d_col, n_vec - 1, 1, d_tail, s));
 		std::vector<PT> tail(VEC);
 		CUDA_TRY(cudaMemcpyAsync(tail.data(), d_tail, VEC * sizeof(PT), cudaMemcpyDeviceToHost, s));
@@ -432,7 +494,7 @@ int alpb200_decode_sum_f32(const alpb200_column* col, uint64_t first, uint64_t n
 	return launch_decode_sum<float>(col, first, n, d_sum, stream);
 }
 
-int alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes) {
+int alpb200_ctx_create_ex(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes, uint64_t packed_capacity, uint64_t exc_capacity) {
 	if (!out || max_vectors == 0 || max_vectors > (1ull << 22) || (value_bytes != 8 && value_bytes != 4)) {
 		return fail(ALPB200_EINVAL, "ctx_create: bad argument (max_vectors in 1..2^22, value_bytes 8 or 4)");
 	}
@@ -441,18 +503,23 @@ int alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int 
 		cudaGetLastError();
 		return fail(ALPB200_ENODEVICE, "no CUDA device is visible; alp_b200 has no CPU fallback");
 	}
-	CUDA_TRY(cudaSetDevice(device));
+	DeviceGuard guard(device);
+	if (!guard.ok) { return fail(ALPB200_ECUDA, "ctx_create: cannot select the device"); }
 	alpb200_ctx* c = new (std::nothrow) alpb200_ctx();
 	if (!c) { return fail(ALPB200_EINVAL, "ctx_create: out of host memory"); }
 	c->device      = device;
 	c->value_bytes = value_bytes;
 	c->max_vectors = max_vectors;
 	const uint64_t n_rg = (max_vectors + ALPB200_ROWGROUP_VECTORS - 1) / ALPB200_ROWGROUP_VECTORS;
-	c->packed_capacity  = max_vectors * ((value_bytes == 8 ? 66ull : 35ull) * 128ull);
-	c->exc_capacity     = max_vectors * VEC;
+	// staging for the compressed column: what the caller says its columns need (an overflow is reported as
+	// ALPB200_ECAPACITY, nothing is written out of bounds), else the worst case — every vector ALP_RD at full width with
+	// 1024 exceptions, ~27 bytes per f64 value, which only a caller that cannot bound its data should pay for
+	const uint64_t worst_packed = max_vectors * ((value_bytes == 8 ? 66ull : 35ull) * 128ull), worst_exc = max_vectors * VEC;
+	c->packed_capacity  = packed_capacity ? std::min<uint64_t>(worst_packed, (packed_capacity + 127ull) & ~127ull) : worst_packed;
+	c->exc_capacity     = exc_capacity ? std::min<uint64_t>(worst_exc, exc_capacity) : worst_exc;
 	cudaError_t err     = cudaSuccess;
 	auto        alloc   = [&](void** p, size_t bytes) {
-        if (err == cudaSuccess) { err = cudaMalloc(p, bytes); }
+        if (err == cudaSuccess) { err = cudaMalloc(p, bytes ? bytes : 16); }
 	};
 	alloc(&c->d_values, max_vectors * VEC * value_bytes);
 	alloc(reinterpret_cast<void**>(&c->d_meta), max_vectors * sizeof(alpb200_vec_meta));
@@ -474,16 +541,24 @@ int alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int 
 	}
 	if (err != cudaSuccess) {
 		ctx_release(c);
+		cudaGetLastError();
 		return fail(ALPB200_ECUDA, "ctx_create: %s", cudaGetErrorString(err));
 	}
 	*out = c;
 	return ALPB200_OK;
+}
+int alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes) {
+	return alpb200_ctx_create_ex(out, device, max_vectors, value_bytes, 0, 0);
 }
 void alpb200_ctx_destroy(alpb200_ctx* ctx) { ctx_release(ctx); }
 int  alpb200_ctx_set_option(alpb200_ctx* ctx, int option, int value) {
 	if (!ctx) { return fail(ALPB200_EINVAL, "ctx_set_option: null context"); }
 	switch (option) {
 	case ALPB200_OPT_UNORDERED: ctx->unordered = value != 0; return ALPB200_OK;
+	case ALPB200_OPT_CHUNKS:
+		if (value < 1 || value > MAX_CHUNKS) { return fail(ALPB200_EINVAL, "ctx_set_option: ALPB200_OPT_CHUNKS must be in 1..16"); }
+		ctx->chunks = (uint64_t)value;
+		return ALPB200_OK;
 	default: return fail(ALPB200_EINVAL, "ctx_set_option: unknown option");
 	}
 }
@@ -498,6 +573,16 @@ int alpb200_decompress_host_f64(alpb200_ctx* ctx, const alpb200_column* h_col, d
 int alpb200_decompress_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, float* h_out) { return decompress_host<float>(ctx, h_col, h_out); }
 int alpb200_sum_host_f64(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_sum) { return sum_host<double>(ctx, h_col, h_sum); }
 int alpb200_sum_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_sum) { return sum_host<float>(ctx, h_col, h_sum); }
+
+int alpb200_column_validate_host(const alpb200_column* h_col, int value_bytes) {
+	if (!h_col || (value_bytes != 8 && value_bytes != 4)) { return fail(ALPB200_EINVAL, "column_validate_host: bad argument"); }
+	if (h_col->n_vectors == 0) { return ALPB200_OK; }
+	if (!h_col->meta || !h_col->packed || !h_col->exc_val || !h_col->exc_pos) { return fail(ALPB200_EINVAL, "column_validate_host: null array"); }
+	const uint64_t n_out = h_col->n_values ? h_col->n_values : h_col->n_vectors * VEC;
+	if (n_out > h_col->n_vectors * VEC || n_out + VEC <= h_col->n_vectors * VEC) { return fail(ALPB200_EINVAL, "column_validate_host: n_values does not match n_vectors"); }
+	const ChunkRange cr = chunk_range(h_col->meta, 0, h_col->n_vectors, value_bytes, h_col);
+	return check_host_column(h_col, cr, "column_validate_host");
+}
 
 void* alpb200_host_alloc(size_t bytes) {
 	void* p = nullptr;

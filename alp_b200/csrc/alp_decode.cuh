@@ -43,6 +43,8 @@ struct ColView {
 	const uint8_t*          packed;
 	const void*             exc_val;
 	const uint16_t*         exc_pos;
+	uint64_t                packed_capacity;  // bytes; 0 = unknown (no bounds check on the records' offsets)
+	uint64_t                exc_capacity;     // slots; 0 = unknown
 };
 
 // the 32-byte alpb200_vec_meta record in two 16-byte registers
@@ -68,6 +70,81 @@ __device__ __forceinline__ MetaRegs load_meta(const alpb200_vec_meta* m) {
 	r.a = __ldg(p);
 	r.b = __ldg(p + 1);
 	return r;
+}
+// A record read from a column somebody else produced may be damaged.  Whatever it says, the kernels never touch memory
+// outside the column's arrays, the warp's stage or the vector's 1024 output slots: the exception count is capped at 1024,
+// positions are taken mod 1024 where they are used, a block or exception run that leaves the arrays (capacities known) makes
+// the record an empty one (bw 0, no exceptions), and a block larger than the stage goes through decode_vector_direct.
+// The HOST entry points reject such columns with ALPB200_EINVAL before anything is launched (alpb200_column_validate_host).
+template <typename PT>
+__device__ __forceinline__ MetaRegs sanitize_meta(MetaRegs m, const ColView& col) {
+	constexpr uint32_t T = Traits<PT>::TBITS;
+	const bool     rd    = m.scheme() == ALPB200_SCHEME_ALP_RD;  // anything else is read as ALP
+	uint32_t       cnt   = min(m.exc_cnt(), (uint32_t)VEC);
+	uint32_t       bw    = min(m.bw(), rd ? T - 1 : T);
+	uint32_t       e     = rd ? min(max(m.e(), 1u), 3u) : min(m.e(), (uint32_t)Traits<PT>::MAX_EXP);
+	uint32_t       f     = rd ? m.f() : min(m.f(), e);
+	const uint32_t units = rd ? bw + e : bw;
+	bool           empty = rd && bw < T - 16;  // right_bit_width is T - cut, cut in 1..16 (rd.hpp:95)
+	empty = empty || (col.packed_capacity != 0 && ((uint64_t)m.packed_off() + units) * 128ull > col.packed_capacity);
+	if (empty) { bw = e = f = cnt = 0; }
+	if (col.exc_capacity != 0 && (uint64_t)m.exc_off() + cnt > col.exc_capacity) { cnt = 0; }
+	const uint32_t scheme = rd && !empty ? ALPB200_SCHEME_ALP_RD : ALPB200_SCHEME_ALP;
+	m.b.z = cnt | (scheme << 16) | (bw << 24);
+	m.b.w = (m.b.w & 0xFFFF0000u) | e | (f << 8);
+	return m;
+}
+
+// the bw-bit field at bit offset `bit` of lane `lane` of a T-bit-lane block in GLOBAL memory; never reads past the block
+template <typename UT>
+__device__ __forceinline__ UT field_at_global(const UT* blk, int lane, uint32_t bit, uint32_t bw) {
+	constexpr uint32_t TB = 8 * sizeof(UT), L = 1024 / TB;
+	if (bw == 0) { return 0; }
+	const uint32_t w = bit / TB, sh = bit % TB;
+	UT             v = (UT)(blk[L * w + lane] >> sh);
+	if (sh + bw > TB) { v = (UT)(v | (UT)(blk[L * (w + 1) + lane] << (TB - sh))); }
+	return (UT)(v & low_mask<UT>((int)bw));
+}
+// decoded bit pattern of value p of a vector, straight from global memory, exceptions NOT applied (run-time widths)
+template <typename PT>
+__device__ __forceinline__ typename Traits<PT>::UT value_bits_direct(const ColView& col, const MetaRegs& m, uint32_t p) {
+	using T  = Traits<PT>;
+	using UT = typename T::UT;
+	using ST = typename T::ST;
+	const uint8_t* blk = col.packed + (uint64_t)m.packed_off() * 128u;
+	const UT       d   = field_at_global<UT>(reinterpret_cast<const UT*>(blk), p % T::LANES, (p / T::LANES) * m.bw(), m.bw());
+	if (m.scheme() == ALPB200_SCHEME_ALP) {
+		const UT base = sizeof(PT) == 8 ? (UT)m.base() : (UT)m.a.x;
+		return T::bits(decode_value<PT>((ST)(UT)(d + base), T::fact10(m.f()), T::frac10(m.e())));
+	}
+	const uint32_t idx = field_at_global<uint16_t>(reinterpret_cast<const uint16_t*>(blk + 128u * m.bw()), p & 63, (p >> 6) * m.e(), m.e());
+	return (UT)(((UT)dict_lookup(m.a, idx) << m.bw()) | d);
+}
+// Rare slow path: the vector's block does not fit the warp's stage (a stale max_block_bytes hint): decode + patch straight
+// from global memory.  Small code on purpose (one loop, run-time widths) — it must not cost the hot path registers.
+template <typename PT>
+__device__ __noinline__ void decode_vector_direct(const ColView& col, const MetaRegs& m, PT* out_vec, int t) {
+	using UT = typename Traits<PT>::UT;
+	UT* ov = reinterpret_cast<UT*>(out_vec);
+#pragma unroll 1
+	for (int i = t; i < VEC; i += 32) {
+		ov[i] = value_bits_direct<PT>(col, m, (uint32_t)i);
+	}
+	__syncwarp();
+	const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
+	const uint16_t* ep = col.exc_pos + m.exc_off();
+	const bool      rd = m.scheme() != ALPB200_SCHEME_ALP;
+#pragma unroll 1
+	for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
+		const uint32_t p = ep[i] & (VEC - 1);
+		UT             v = ev[i];
+		if (rd) {  // the true left part replaces the dictionary entry (rd.hpp:172-177)
+			const UT right = field_at_global<UT>(reinterpret_cast<const UT*>(col.packed + (uint64_t)m.packed_off() * 128u), p % Traits<PT>::LANES,
+			                                     (p / Traits<PT>::LANES) * m.bw(), m.bw());
+			v              = (UT)(((v & 0xFFFFu) << m.bw()) | right);
+		}
+		ov[p] = v;
+	}
 }
 
 // ---- ALP, 64-bit lanes -------------------------------------------------------------------------------------------
@@ -115,7 +192,7 @@ __device__ __forceinline__ ExcRegs<UT> load_exceptions(const ColView& col, const
 	x.pos = 0;
 	x.val = 0;
 	if ((uint32_t)t < m.exc_cnt()) {
-		x.pos = __ldg(col.exc_pos + m.exc_off() + t);
+		x.pos = __ldg(col.exc_pos + m.exc_off() + t) & (VEC - 1);  // (a damaged position must not leave the vector)
 		x.val = __ldg(static_cast<const UT*>(col.exc_val) + m.exc_off() + t);
 	}
 	return x;
@@ -148,14 +225,14 @@ __device__ __forceinline__ void patch_alp(const ColView& col, const MetaRegs& m,
 		const uint16_t* ep = col.exc_pos + m.exc_off();
 		for (uint32_t i = t + 32; i < cnt; i += 96) {  // three independent (position, value) loads in flight per lane
 			const uint32_t i1 = i + 32, i2 = i + 64;
-			uint32_t       p0 = ep[i], p1 = 0, p2 = 0;
+			uint32_t       p0 = ep[i] & (VEC - 1), p1 = 0, p2 = 0;
 			UT             v0 = ev[i], v1 = 0, v2 = 0;
 			if (i1 < cnt) {
-				p1 = ep[i1];
+				p1 = ep[i1] & (VEC - 1);
 				v1 = ev[i1];
 			}
 			if (i2 < cnt) {
-				p2 = ep[i2];
+				p2 = ep[i2] & (VEC - 1);
 				v2 = ev[i2];
 			}
 			ov[p0] = v0;
@@ -223,7 +300,7 @@ __device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const Col
 		const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
 		const uint16_t* ep = col.exc_pos + m.exc_off();
 		for (uint32_t i = t + 32; i < cnt; i += 32) {
-			const uint32_t p = ep[i];
+			const uint32_t p = ep[i] & (VEC - 1);
 			ov[p]            = ((ev[i] & 0xFFFFu) << rbw) | rd_right_at(stage, rbw, p, UT());
 		}
 	}
@@ -281,18 +358,20 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 	if (v >= n_vectors) { return; }
 	const alpb200_vec_meta* meta = col.meta + first_vector;
 
-	auto issue = [&](const MetaRegs& m, int s) {
-		const uint32_t bytes = m.block_bytes();
-		if (t == 0 && bytes != 0) {
-			mbar_arrive_expect_tx(&bars[s], bytes);
-			bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
-		}
+	const uint32_t stage_cap = stage_bytes - STAGE_PAD;  // the largest block a stage can take
+	auto           staged    = [&](const MetaRegs& m) { return m.block_bytes() != 0 && m.block_bytes() <= stage_cap; };
+	auto           issue     = [&](const MetaRegs& m, int s) {
+        const uint32_t bytes = m.block_bytes();
+        if (t == 0 && staged(m)) {
+            mbar_arrive_expect_tx(&bars[s], bytes);
+            bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
+        }
 	};
 
-	MetaRegs cur = load_meta(meta + v);
+	MetaRegs cur = sanitize_meta<PT>(load_meta(meta + v), col);
 	bool     has_next = v_next < n_vectors;
 	MetaRegs nxt      = cur;
-	if (has_next) { nxt = load_meta(meta + v_next); }
+	if (has_next) { nxt = sanitize_meta<PT>(load_meta(meta + v_next), col); }
 	issue(cur, 0);
 	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
 	uint32_t    phase = 0;  // bit s: parity the next wait on stage s must see
@@ -306,10 +385,10 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
 		MetaRegs       nn     = nxt;
-		if (has_nn) { nn = load_meta(meta + v_nn); }
+		if (has_nn) { nn = sanitize_meta<PT>(load_meta(meta + v_nn), col); }
 
 		const uint8_t* stg = stage + (size_t)s * stage_bytes;
-		if (cur.block_bytes() != 0) {
+		if (staged(cur)) {
 			mbar_wait(&bars[s], (phase >> s) & 1u);
 			phase ^= 1u << s;
 		}
@@ -320,7 +399,9 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 			__syncwarp();
 			out_vec = tile;
 		}
-		if (cur.scheme() == ALPB200_SCHEME_ALP) {
+		if (cur.block_bytes() > stage_cap) {
+			decode_vector_direct<PT>(col, cur, out_vec, t);  // the block outgrows the stage (stale hint): slow, correct
+		} else if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			decode_alp_vector(stg, cur, out_vec, t);
 			__syncwarp();  // orders the patch stores after the lane-interleaved main stores
 			patch_alp<PT>(col, cur, xcur, out_vec, t);

@@ -14,6 +14,8 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 	if (n == 0) { return ALPB200_OK; }
 	if (!d_out || !col->meta || !col->packed) { return fail(ALPB200_EINVAL, "decode: null argument"); }
 	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0) { return fail(ALPB200_EINVAL, "decode: column.packed must be 128-byte aligned"); }
+	if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) { return fail(ALPB200_EINVAL, "decode: the output buffer must be 16-byte aligned"); }
+	if ((reinterpret_cast<uintptr_t>(col->meta) & 15u) != 0) { return fail(ALPB200_EINVAL, "decode: column.meta must be 16-byte aligned"); }
 	DeviceInfo di;
 	if (int rc = device_info(di)) { return rc; }
 	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
@@ -29,7 +31,7 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 	if (per_sm < 1) { return fail(ALPB200_ECUDA, "decode: kernel does not fit on an SM"); }
 	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
 	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
-	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos, col->packed_capacity, col->exc_capacity};
 	unsigned long long* counter = di.counters + di.next_counter;
 	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
 	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_out, stage, counter);
@@ -44,6 +46,7 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 	if (n == 0) { return ALPB200_OK; }
 	if (!col->meta || !col->packed) { return fail(ALPB200_EINVAL, "decode_sum: null argument"); }
 	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0) { return fail(ALPB200_EINVAL, "decode_sum: column.packed must be 128-byte aligned"); }
+	if ((reinterpret_cast<uintptr_t>(col->meta) & 15u) != 0) { return fail(ALPB200_EINVAL, "decode_sum: column.meta must be 16-byte aligned"); }
 	DeviceInfo di;
 	if (int rc = device_info(di)) { return rc; }
 	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
@@ -52,7 +55,7 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 	// The scan is bound by what the resident warps can unpack, so the block shape is the one that puts the most warps on
 	// an SM: 8 warps per block while two stages per warp are small (narrow ALP blocks), fewer when they are wide (ALP_RD on
 	// doubles: 2 x 7.3 KiB per warp would leave ONE 8-warp block per SM; 5-warp blocks fit three).
-	ColView             view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	ColView             view {col->meta, col->packed, col->exc_val, col->exc_pos, col->packed_capacity, col->exc_capacity};
 	unsigned long long* counter = di.counters + di.next_counter;
 	cudaStream_t        s       = static_cast<cudaStream_t>(stream);
 	int                 best_w = 0, best_per_sm = 0;

@@ -116,6 +116,29 @@ __device__ __forceinline__ double sum_rd_vector(const uint8_t* stage, const Meta
 	return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
+// rare slow path (see decode_vector_direct): the thread's share of the vector's sum straight from global memory
+template <typename PT>
+__device__ __noinline__ double sum_vector_direct(const ColView& col, const MetaRegs& m, int t) {
+	using UT   = typename Traits<PT>::UT;
+	double acc = 0.0;
+#pragma unroll 1
+	for (int i = t; i < VEC; i += 32) {
+		acc += (double)Traits<PT>::from_bits(value_bits_direct<PT>(col, m, (uint32_t)i));
+	}
+	const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
+	const uint16_t* ep = col.exc_pos + m.exc_off();
+	const bool      rd = m.scheme() != ALPB200_SCHEME_ALP;
+#pragma unroll 1
+	for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
+		const uint32_t p    = ep[i] & (VEC - 1);
+		const UT       fill = value_bits_direct<PT>(col, m, p);
+		UT             v    = ev[i];
+		if (rd) { v = (UT)(((v & 0xFFFFu) << m.bw()) | (fill & low_mask<UT>((int)m.bw()))); }
+		acc += (double)Traits<PT>::from_bits(v) - (double)Traits<PT>::from_bits(fill);
+	}
+	return acc;
+}
+
 // register allocation limited for 32 resident warps per SM (64 registers, no spills): against 24 x 80 registers the f64
 // scan gains 4-8 % (0.293 -> 0.280 ms per 2^29 values on config 2)
 template <typename PT, int WARPS>
@@ -154,17 +177,19 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 	uint64_t v = take(), v_next = take();
 	if (v >= n_vectors) { return; }
 	const alpb200_vec_meta* meta = col.meta + first_vector;
-	auto issue = [&](const MetaRegs& m, int s) {
-		const uint32_t bytes = m.block_bytes();
-		if (t == 0 && bytes != 0) {
-			mbar_arrive_expect_tx(&bars[s], bytes);
-			bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
-		}
+	const uint32_t stage_cap = stage_bytes - STAGE_PAD;
+	auto           staged    = [&](const MetaRegs& m) { return m.block_bytes() != 0 && m.block_bytes() <= stage_cap; };
+	auto           issue     = [&](const MetaRegs& m, int s) {
+        const uint32_t bytes = m.block_bytes();
+        if (t == 0 && staged(m)) {
+            mbar_arrive_expect_tx(&bars[s], bytes);
+            bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
+        }
 	};
-	MetaRegs cur = load_meta(meta + v);
+	MetaRegs cur = sanitize_meta<PT>(load_meta(meta + v), col);
 	bool     has_next = v_next < n_vectors;
 	MetaRegs nxt      = cur;
-	if (has_next) { nxt = load_meta(meta + v_next); }
+	if (has_next) { nxt = sanitize_meta<PT>(load_meta(meta + v_next), col); }
 	issue(cur, 0);
 	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
 	uint32_t    phase = 0;
@@ -179,26 +204,28 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
 		MetaRegs       nn     = nxt;
-		if (has_nn) { nn = load_meta(meta + v_nn); }
+		if (has_nn) { nn = sanitize_meta<PT>(load_meta(meta + v_nn), col); }
 		const uint8_t* stg = stage + (size_t)s * stage_bytes;
-		if (cur.block_bytes() != 0) {
+		if (staged(cur)) {
 			mbar_wait(&bars[s], (phase >> s) & 1u);
 			phase ^= 1u << s;
 		}
 		const uint32_t  cnt = cur.exc_cnt();
 		const UT*       ev  = static_cast<const UT*>(col.exc_val) + cur.exc_off();
 		const uint16_t* ep  = col.exc_pos + cur.exc_off();
-		if (cur.scheme() == ALPB200_SCHEME_ALP) {
+		if (cur.block_bytes() > stage_cap) {
+			acc += sum_vector_direct<PT>(col, cur, t);  // the block outgrows the stage (stale hint): slow, correct
+		} else if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			acc += sum_alp_vector(stg, cur, t, PT());
 			for (uint32_t i = t; i < cnt; i += 32) {  // exception: + true value - decoded fill value
-				const uint32_t p   = i < 32 ? xcur.pos : ep[i];
+				const uint32_t p   = i < 32 ? xcur.pos : (ep[i] & (VEC - 1));
 				const UT       val = i < 32 ? xcur.val : ev[i];
 				acc += (double)Traits<PT>::from_bits(val) - alp_value_at(stg, cur, p, PT());
 			}
 		} else {
 			acc += sum_rd_vector<PT>(stg, cur, t);
 			for (uint32_t i = t; i < cnt; i += 32) {
-				const uint32_t p    = i < 32 ? xcur.pos : ep[i];
+				const uint32_t p    = i < 32 ? xcur.pos : (ep[i] & (VEC - 1));
 				const uint32_t left = (uint32_t)((i < 32 ? xcur.val : ev[i]) & 0xFFFFu);
 				acc += rd_value<PT>(stg, cur, p, true, left) - rd_value<PT>(stg, cur, p, false, 0);
 			}

@@ -187,46 +187,84 @@ def time_cpu(fn, budget_s, max_reps=50):
             return dt / reps, reps
 
 
-def cpu_legs(checker, x_host, threads, budget_s, ref_col=None):
-    """The reference's CPU path on a host sample of a column, all host threads: decode (falp + patch_exceptions, or
-    unffor x2 + rd decode), encode with given states (encode + analyze_ffor + ffor / rd encode + 2x ffor,
-    test/test_alp_sample.cpp:141-145,164-166), row-group init + encode, and the scan query (alp_func + aggr_plus,
-    q1.cpp:63-100).  GB/s are bytes of uncompressed values per second."""
-    from alp_b200 import _abi
+def ref_bench_binary():
+    """oracle/_ref/ref_bench_v{4,3}: the reference compiled as an executable (oracle/ref_bench_main.cpp), or None."""
+    from oracle import pyoracle
 
-    n = x_host.shape[0] // 1024 * 1024
-    x_host = x_host[:n]
-    vb = x_host.dtype.itemsize
+    names = ["ref_bench_v4", "ref_bench_v3"] if pyoracle._cpu_has_avx512() else ["ref_bench_v3"]
+    for name in names:
+        path = os.path.join(ROOT, "oracle", "_ref", name)
+        if os.path.exists(path) and os.access(path, os.X_OK):
+            return path
+    return None
+
+
+def cpu_legs(kind, n_values, threads, budget_s, steps=0, warmup=1, x_host=None):
+    """The reference's CPU path on the first n_values values of a synthetic column, all host threads: decode (falp +
+    patch_exceptions, or unffor x2 + rd decode), encode with given states (encode + analyze_ffor + ffor / rd encode + 2x ffor,
+    test/test_alp_sample.cpp:141-145,164-166), row-group init, and the scan query (alp_func + aggr_plus, q1.cpp:63-100).
+    Runs oracle/_ref/ref_bench_* (the reference as an executable: its thread-local encoder scratch is slow inside a dlopen'ed
+    library); without it, the same drivers in-process through oracle/pyoracle.py.  GB/s = bytes of uncompressed values per second."""
+    vb = SIDE_CONFIGS[kind][1]
+    n = int(n_values) // 1024 * 1024
     nbytes = n * vb
-    units = 67 if vb == 8 else 35
-    col = _abi.HostColumn(n // 1024, vb, (n // 1024 + threads * 100) * units * 128, n + threads * 102400)
-    states = checker.bench_init(x_host, n_threads=threads)
-    t_init, _ = time_cpu(lambda: checker.bench_init(x_host, n_threads=threads, states=states), budget_s / 4)
-    t_enc, _ = time_cpu(lambda: checker.bench_encode(x_host, n_threads=threads, states=states, col=col), budget_s / 4)
-    out = np.empty(n, dtype=x_host.dtype)
-    t_dec, reps = time_cpu(lambda: checker.decode_column(col, n_threads=threads, out=out), budget_s / 4, 200)
-    ok = out.tobytes() == x_host.tobytes()
-    got = [0.0]
+    exe = ref_bench_binary()
+    if exe is not None:
+        cmd = [exe, "--kind", str(kind), "--values", str(n), "--threads", str(threads), "--seconds", "%.3f" % budget_s]
+        if steps > 0:
+            cmd += ["--steps", str(steps), "--warmup", str(warmup)]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+        if res.returncode != 0:
+            raise RuntimeError("ref_bench failed (%d): %s" % (res.returncode, res.stderr[-500:]))
+        r = json.loads(res.stdout.strip().splitlines()[-1])
+        t_dec, t_enc, t_init, t_scan = r["decode_s"], r["encode_s"], r["init_s"], r["scan_s"]
+        leg = {"kind": "reference", "build": r["build"], "round_trip_bit_exact": bool(r["round_trip_bit_exact"]), "decode_reps": r["decode_reps"],
+               "decode_single_thread_GBps": vb / r["decode_single_thread_s_per_value"] / 1e9, "scan_sum": r["scan_sum"], "runner": os.path.relpath(exe, ROOT)}
+    else:
+        from alp_b200 import _abi
+        from oracle import pyoracle
 
-    def scan():
-        got[0] = checker.sum_column(col, n_threads=threads)
+        checker = pyoracle.best()
+        if x_host is None:
+            x_host = pyoracle.generate(n, kind, n_threads=threads)
+        x_host = x_host[:n]
+        units = 67 if vb == 8 else 35
+        col = _abi.HostColumn(n // 1024, vb, (n // 1024 + threads * 100) * units * 128, n + threads * 102400)
+        states = checker.bench_init(x_host, n_threads=threads)
+        t_init, _ = time_cpu(lambda: checker.bench_init(x_host, n_threads=threads, states=states), budget_s / 4)
+        t_enc, _ = time_cpu(lambda: checker.bench_encode(x_host, n_threads=threads, states=states, col=col), budget_s / 4)
+        out = np.empty(n, dtype=x_host.dtype)
+        if steps > 0:
+            for _ in range(max(1, warmup)):
+                checker.decode_column(col, n_threads=threads, out=out)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                checker.decode_column(col, n_threads=threads, out=out)
+            t_dec, reps = (time.perf_counter() - t0) / steps, steps
+        else:
+            t_dec, reps = time_cpu(lambda: checker.decode_column(col, n_threads=threads, out=out), budget_s / 4, 200)
+        ok = out.tobytes() == x_host.tobytes()
+        got = [0.0]
 
-    t_scan, _ = time_cpu(scan, budget_s / 4)
-    t_dec1, _ = time_cpu(lambda: checker.decode_column(col, n=min(col.n_vectors, 4096), n_threads=1, out=out), 0.3)
-    return {
+        def scan():
+            got[0] = checker.sum_column(col, n_threads=threads)
+
+        t_scan, _ = time_cpu(scan, budget_s / 4)
+        n1 = min(col.n_vectors, 4096)
+        t_dec1, _ = time_cpu(lambda: checker.decode_column(col, n=n1, n_threads=1, out=out), 0.3)
+        leg = {"kind": checker.kind, "build": checker.build_info, "round_trip_bit_exact": bool(ok), "decode_reps": reps,
+               "decode_single_thread_GBps": n1 * 1024 * vb / t_dec1 / 1e9, "scan_sum": got[0], "runner": "in-process (oracle/pyoracle.py)"}
+    leg.update({
         "cores": threads,
-        "kind": checker.kind,
-        "sample": "first 2^%.2f values of the same column (%s)" % (np.log2(max(n, 1)), checker.build_info),
-        "round_trip_bit_exact": bool(ok),
+        "sample": "first 2^%.2f values of the same column" % np.log2(max(n, 1)),
+        "decode_ms": t_dec * 1e3,
         "decode_GBps": nbytes / t_dec / 1e9,
-        "decode_reps": reps,
-        "decode_single_thread_GBps": min(col.n_vectors, 4096) * 1024 * vb / t_dec1 / 1e9,
         "encode_GBps": nbytes / t_enc / 1e9,
         "rowgroup_init_ms": t_init * 1e3,
         "init_plus_encode_GBps": nbytes / (t_enc + t_init) / 1e9,
         "scan_sum_GBps": nbytes / t_scan / 1e9,
-        "scan_sum": got[0],
-    }
+    })
+    return leg
 
 
 class JsonChannel:
@@ -250,31 +288,18 @@ def run_reference(args):
     if rank != 0:
         return
     channel = JsonChannel()
-    from oracle import pyoracle  # loads only oracle/ libraries: this arm never maps libalp_b200.so
-
-    checker = pyoracle.best()
     threads = host_threads()
     n = args.values // 1024 * 1024
-    x = pyoracle.generate(n, KIND, n_threads=threads)
-    col = checker.bench_encode(x, n_threads=threads)  # untimed set-up: the compressed column (init + encode per row-group)
-    out = np.empty(n, dtype=np.float64)
-    for _ in range(max(1, args.warmup)):
-        checker.decode_column(col, n_threads=threads, out=out)
-    verified = out.tobytes() == x.tobytes()
+    # the headline leg: K timed decode passes over the WHOLE column after W warm-up passes (encode / init / scan ride along)
+    head = cpu_legs(KIND, n, threads, args.cpu_seconds, steps=args.steps, warmup=max(1, args.warmup))
+    verified = head["round_trip_bit_exact"]
     assert verified, "the reference's decode of its own column differs from the original"
-    times = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        checker.decode_column(col, n_threads=threads, out=out)
-        times.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(times) / len(times)
+    ms = head["decode_ms"]
     value = n * 8.0 / (ms * 1e-3) / 1e9
-    del out, col
-    side = {}
+    side = {str(KIND): dict(head, label=SIDE_CONFIGS[KIND][0])}
     for kind, (label, vb, rel) in SIDE_CONFIGS.items():
-        ns = int(min(n * rel, CPU_SAMPLE_VALUES)) // 1024 * 1024
-        xs = x[:ns] if kind == KIND else pyoracle.generate(ns, kind, n_threads=threads)
-        side[str(kind)] = dict(cpu_legs(checker, xs, threads, args.cpu_seconds / 3), label=label)
+        if kind != KIND:
+            side[str(kind)] = dict(cpu_legs(kind, min(n * rel, CPU_SAMPLE_VALUES), threads, args.cpu_seconds), label=label)
     sample = "the whole 2^%.2f-value column, all vectors, decode = falp + patch_exceptions" % np.log2(max(n, 1))
     line = {
         "impl": "reference",
@@ -292,7 +317,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": workload_config(n),
         "verified_bit_exact": bool(verified),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": checker.kind, "sample": sample, "build": checker.build_info},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": head["kind"], "sample": sample, "build": head["build"], "runner": head["runner"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "configs": side,
@@ -357,7 +382,7 @@ def compress_on_device(x, dev, reps=3):
     return col, t
 
 
-def config_block(kind, n, dev, rank, peak, steps, cpu_checker, cpu_seconds):
+def config_block(kind, n, dev, rank, peak, steps, with_cpu, cpu_seconds):
     """One BASELINE config on this rank's GPU: device-timed encode / init / decode / scan with roofline fractions and a
     bit-exact check; at N = 1 the reference's CPU numbers for a bounded slice of the same column beside them."""
     import torch
@@ -410,9 +435,9 @@ def config_block(kind, n, dev, rank, peak, steps, cpu_checker, cpu_seconds):
         "scan_sum": {"ms": scan_ms, "GBps_decoded_equivalent": rate(scan_ms, n * vb), "read_GBps": rate(scan_ms, read_bytes),
                      "roofline_frac": rate(scan_ms, read_bytes) / peak, "rel_err_vs_torch_sum": abs(got - want) / max(abs(want), 1e-300)},
     }
-    if cpu_checker is not None:
+    if with_cpu:
         ns = min(n, CPU_SAMPLE_VALUES)
-        block["cpu"] = cpu_legs(cpu_checker, x[:ns].cpu().numpy(), host_threads(), cpu_seconds)
+        block["cpu"] = cpu_legs(kind, ns, host_threads(), cpu_seconds, x_host=None if ref_bench_binary() else x[:ns].cpu().numpy())
         c = block["cpu"]
         block["vs_cpu"] = {
             "decode": block["decode"]["GBps"] / c["decode_GBps"],
@@ -500,11 +525,7 @@ def main():
     n_vec = n // _abi.VECTOR_SIZE
     launches = 0
     peak, peak_src = measured_peak()
-    cpu_checker = None
-    if rank == 0 and world == 1:
-        from oracle import pyoracle
-
-        cpu_checker = pyoracle.best()
+    with_cpu = rank == 0 and world == 1  # the CPU legs run beside the GPU numbers at N = 1 only
 
     def barrier():
         if world > 1:
@@ -516,13 +537,13 @@ def main():
     if not args.no_side:
         for kind in (3, 4):
             nk = int(n * SIDE_CONFIGS[kind][2]) // 1024 * 1024
-            block, xk, colk, _, _ = config_block(kind, nk, dev, rank, peak, args.steps, cpu_checker, args.cpu_seconds)
+            block, xk, colk, _, _ = config_block(kind, nk, dev, rank, peak, args.steps, with_cpu, args.cpu_seconds)
             configs[str(kind)] = block
             del xk, colk
             torch.cuda.empty_cache()
 
     # ---- untimed set-up of the headline: this rank's shard of the global column, compressed on the device ----
-    block2, x, col, meta, read_bytes = config_block(KIND, n, dev, rank, peak, args.steps, cpu_checker, args.cpu_seconds)
+    block2, x, col, meta, read_bytes = config_block(KIND, n, dev, rank, peak, args.steps, with_cpu, args.cpu_seconds)
     configs[str(KIND)] = block2
     verified = block2["verified_bit_exact"]
     algo_bytes = read_bytes + n * 8
@@ -670,7 +691,7 @@ def main():
         if "cpu" in block2:
             c = block2["cpu"]
             cpu = {"value": c["decode_GBps"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "single_thread_value": c["decode_single_thread_GBps"],
-                   "sample": c["sample"] + ", decoded %d times (falp + patch_exceptions)" % c["decode_reps"]}
+                   "sample": c["sample"] + ", decoded %d times (falp + patch_exceptions; %s)" % (c["decode_reps"], c["build"]), "runner": c["runner"]}
         line = {
             "metric": METRIC,
             "value": value,

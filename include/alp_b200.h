@@ -209,12 +209,19 @@ int alpb200_decode_sum_f32(const alpb200_column* col, uint64_t first_vector, uin
  * ---------------------------------------------------------------------------------------------- */
 typedef struct alpb200_ctx alpb200_ctx;
 
-/* max_vectors: the largest column (in vectors) a call will pass; value_bytes: 8 or 4. */
+/* max_vectors: the largest column (in vectors) a call will pass (at most 2^22 = 2^32 values); value_bytes: 8 or 4.
+ * The context's device staging is sized for the worst case a column can reach (every vector ALP_RD at full width with 1024
+ * exceptions: ~27 bytes per f64 value).  alpb200_ctx_create_ex takes the caller's own bound on the compressed column instead
+ * — packed bytes and exception slots, 0 = worst case; a column that outgrows them fails with ALPB200_ECAPACITY. */
 int  alpb200_ctx_create(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes);
+int  alpb200_ctx_create_ex(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes, uint64_t packed_capacity,
+                           uint64_t exc_capacity);
 void alpb200_ctx_destroy(alpb200_ctx* ctx);
 /* Context options.  ALPB200_OPT_UNORDERED (0 | 1, default 0): alpb200_compress_host_* encodes with the
- * completion-order layout (alpb200_encode_unordered_*). */
+ * completion-order layout (alpb200_encode_unordered_*).  ALPB200_OPT_CHUNKS (1..16, default 16): how many chunks the
+ * host entry points cut a column into (transfers of neighbouring chunks overlap the kernels of the current one). */
 #define ALPB200_OPT_UNORDERED 1
+#define ALPB200_OPT_CHUNKS 2
 int  alpb200_ctx_set_option(alpb200_ctx* ctx, int option, int value);
 
 /* Compress a host column of n_values values (any length: a partial last vector is padded on the device with the
@@ -233,6 +240,13 @@ int alpb200_decompress_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, f
  * as one call.  Only the compressed bytes cross PCIe.  A padded tail (n_values < n_vectors * 1024) is excluded. */
 int alpb200_sum_host_f64(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_sum);
 int alpb200_sum_host_f32(alpb200_ctx* ctx, const alpb200_column* h_col, double* h_sum);
+/* Checks a HOST column container the way alpb200_decompress_host_* / alpb200_sum_host_* do before they launch anything:
+ * every record well formed (scheme ALP or ALP_RD; bw <= lane width, resp. lane width - 16 <= right width < lane width;
+ * exponent / factor / left width / dictionary size in range; at most 1024 exceptions, every position < 1024) and pointing
+ * inside the container's arrays.  ALPB200_EINVAL otherwise — a damaged or truncated stored column is rejected, not decoded.
+ * (The device entry points cannot afford that pass; their kernels instead clamp whatever a record says so that nothing
+ * outside the column's arrays or the output vector is ever touched.) */
+int alpb200_column_validate_host(const alpb200_column* h_col, int value_bytes);
 /* Page-locked host memory for the buffers handed to the *_host entry points (pageable buffers also work, slower). */
 void* alpb200_host_alloc(size_t bytes);
 void  alpb200_host_free(void* p);

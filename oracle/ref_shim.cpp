@@ -436,6 +436,7 @@ int ref_sum_column(const alpb200_column* col, size_t first, size_t n, int n_thre
 
 } // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char* alpref_build_info() {
@@ -567,3 +568,4 @@ int alpref_sum_column_f32(const alpb200_column* col, size_t first, size_t n, int
 
 
 } // extern "C"
+#pragma GCC visibility pop
