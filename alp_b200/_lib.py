@@ -50,6 +50,7 @@ SIGNATURES = {
     "alpb200_ctx_create": ([_P, _c.c_int, _c.c_uint64, _c.c_int], _c.c_int),
     "alpb200_ctx_create_ex": ([_P, _c.c_int, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_uint64], _c.c_int),
     "alpb200_column_validate_host": ([_P, _c.c_int], _c.c_int),
+    "alpb200_column_validate_device": ([_P, _c.c_int, _P, _P], _c.c_int),
     "alpb200_ctx_destroy": ([_P], None),
     "alpb200_ctx_set_option": ([_P, _c.c_int, _c.c_int], _c.c_int),
     "alpb200_compress_host_f64": ([_P, _P, _c.c_uint64, _P], _c.c_int),

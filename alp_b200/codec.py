@@ -116,6 +116,16 @@ class DeviceColumn:
         col.max_block_bytes = int(h.totals[3])
         return col
 
+    def validate(self):
+        """alpb200_column_validate_device: raises AlpError(EINVAL) for a malformed column; on success also renews the
+        decode hint (max_block_bytes) from the records.  Synchronises the current stream."""
+        st = self.as_struct()
+        widest = ctypes.c_uint64(0)
+        with torch.cuda.device(self.device):
+            check(lib.alpb200_column_validate_device(ctypes.byref(st), self.value_bytes, ctypes.byref(widest), _stream_ptr(self.device)))
+        self.max_block_bytes = int(widest.value)
+        return self
+
     def shard(self, first, n):
         """A view of vectors [first, first+n) as a column of its own (metadata copied and rebased on the host side
         is not needed: offsets stay absolute and the arrays are shared)."""

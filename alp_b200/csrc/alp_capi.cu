@@ -584,6 +584,10 @@ int alpb200_column_validate_host(const alpb200_column* h_col, int value_bytes) {
 	return check_host_column(h_col, cr, "column_validate_host");
 }
 
+int alpb200_column_validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_block_bytes, void* stream) {
+	return validate_device(col, value_bytes, h_max_block_bytes, stream);
+}
+
 void* alpb200_host_alloc(size_t bytes) {
 	void* p = nullptr;
 	if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {

@@ -43,8 +43,6 @@ struct ColView {
 	const uint8_t*          packed;
 	const void*             exc_val;
 	const uint16_t*         exc_pos;
-	uint64_t                packed_capacity;  // bytes; 0 = unknown (no bounds check on the records' offsets)
-	uint64_t                exc_capacity;     // slots; 0 = unknown
 };
 
 // the 32-byte alpb200_vec_meta record in two 16-byte registers
@@ -71,27 +69,14 @@ __device__ __forceinline__ MetaRegs load_meta(const alpb200_vec_meta* m) {
 	r.b = __ldg(p + 1);
 	return r;
 }
-// A record read from a column somebody else produced may be damaged.  Whatever it says, the kernels never touch memory
-// outside the column's arrays, the warp's stage or the vector's 1024 output slots: the exception count is capped at 1024,
-// positions are taken mod 1024 where they are used, a block or exception run that leaves the arrays (capacities known) makes
-// the record an empty one (bw 0, no exceptions), and a block larger than the stage goes through decode_vector_direct.
-// The HOST entry points reject such columns with ALPB200_EINVAL before anything is launched (alpb200_column_validate_host).
-template <typename PT>
-__device__ __forceinline__ MetaRegs sanitize_meta(MetaRegs m, const ColView& col) {
-	constexpr uint32_t T = Traits<PT>::TBITS;
-	const bool     rd    = m.scheme() == ALPB200_SCHEME_ALP_RD;  // anything else is read as ALP
-	uint32_t       cnt   = min(m.exc_cnt(), (uint32_t)VEC);
-	uint32_t       bw    = min(m.bw(), rd ? T - 1 : T);
-	uint32_t       e     = rd ? min(max(m.e(), 1u), 3u) : min(m.e(), (uint32_t)Traits<PT>::MAX_EXP);
-	uint32_t       f     = rd ? m.f() : min(m.f(), e);
-	const uint32_t units = rd ? bw + e : bw;
-	bool           empty = rd && bw < T - 16;  // right_bit_width is T - cut, cut in 1..16 (rd.hpp:95)
-	empty = empty || (col.packed_capacity != 0 && ((uint64_t)m.packed_off() + units) * 128ull > col.packed_capacity);
-	if (empty) { bw = e = f = cnt = 0; }
-	if (col.exc_capacity != 0 && (uint64_t)m.exc_off() + cnt > col.exc_capacity) { cnt = 0; }
-	const uint32_t scheme = rd && !empty ? ALPB200_SCHEME_ALP_RD : ALPB200_SCHEME_ALP;
-	m.b.z = cnt | (scheme << 16) | (bw << 24);
-	m.b.w = (m.b.w & 0xFFFF0000u) | e | (f << 8);
+// What the hot loops guarantee whatever a record says: a block larger than the warp's stage is never bulk-copied (it takes
+// decode_vector_direct instead — a stale max_block_bytes hint stays harmless), at most 1024 exceptions are applied and an
+// exception position is taken mod 1024, so a patch never leaves the vector.  Everything else about a record (bit width vs
+// lane width, exponent / factor range, offsets inside the arrays) is the business of alpb200_column_validate_host /
+// alpb200_column_validate_device: the batched decoders assume a well-formed column, as the reference's primitives do
+// (a full per-record check in this loop cost 2-14 % of the decode throughput on B200).
+__device__ __forceinline__ MetaRegs clamp_meta(MetaRegs m) {
+	m.b.z = (m.b.z & 0xFFFF0000u) | min(m.b.z & 0xFFFFu, (uint32_t)VEC);
 	return m;
 }
 
@@ -105,14 +90,25 @@ __device__ __forceinline__ UT field_at_global(const UT* blk, int lane, uint32_t 
 	if (sh + bw > TB) { v = (UT)(v | (UT)(blk[L * (w + 1) + lane] << (TB - sh))); }
 	return (UT)(v & low_mask<UT>((int)bw));
 }
+// (slow path only) widths and table indices forced into range: shifts and table reads stay defined
+template <typename PT>
+__device__ __forceinline__ uint4 clamp_widths(uint4 b) {
+	constexpr uint32_t T  = Traits<PT>::TBITS;
+	const bool         rd = ((b.z >> 16) & 0xFFu) == ALPB200_SCHEME_ALP_RD;
+	const uint32_t     bw = min(b.z >> 24, rd ? T - 1 : T);
+	const uint32_t     e  = rd ? min(max(b.w & 0xFFu, 1u), 15u) : min(b.w & 0xFFu, (uint32_t)Traits<PT>::MAX_EXP);
+	const uint32_t     f  = rd ? ((b.w >> 8) & 0xFFu) : min((b.w >> 8) & 0xFFu, e);
+	b.z = (b.z & 0x00FFFFFFu) | (bw << 24);
+	b.w = (b.w & 0xFFFF0000u) | e | (f << 8);
+	return b;
+}
 // decoded bit pattern of value p of a vector, straight from global memory, exceptions NOT applied (run-time widths)
 template <typename PT>
-__device__ __forceinline__ typename Traits<PT>::UT value_bits_direct(const ColView& col, const MetaRegs& m, uint32_t p) {
+__device__ __forceinline__ typename Traits<PT>::UT value_bits_direct(const uint8_t* blk, const MetaRegs& m, uint32_t p) {
 	using T  = Traits<PT>;
 	using UT = typename T::UT;
 	using ST = typename T::ST;
-	const uint8_t* blk = col.packed + (uint64_t)m.packed_off() * 128u;
-	const UT       d   = field_at_global<UT>(reinterpret_cast<const UT*>(blk), p % T::LANES, (p / T::LANES) * m.bw(), m.bw());
+	const UT d = field_at_global<UT>(reinterpret_cast<const UT*>(blk), p % T::LANES, (p / T::LANES) * m.bw(), m.bw());
 	if (m.scheme() == ALPB200_SCHEME_ALP) {
 		const UT base = sizeof(PT) == 8 ? (UT)m.base() : (UT)m.a.x;
 		return T::bits(decode_value<PT>((ST)(UT)(d + base), T::fact10(m.f()), T::frac10(m.e())));
@@ -121,26 +117,29 @@ __device__ __forceinline__ typename Traits<PT>::UT value_bits_direct(const ColVi
 	return (UT)(((UT)dict_lookup(m.a, idx) << m.bw()) | d);
 }
 // Rare slow path: the vector's block does not fit the warp's stage (a stale max_block_bytes hint): decode + patch straight
-// from global memory.  Small code on purpose (one loop, run-time widths) — it must not cost the hot path registers.
+// from global memory.  Small code on purpose (one loop, run-time widths), and every argument travels BY VALUE: a reference
+// to the caller's record would force it out of registers in the hot loop.
 template <typename PT>
-__device__ __noinline__ void decode_vector_direct(const ColView& col, const MetaRegs& m, PT* out_vec, int t) {
+__device__ __noinline__ void decode_vector_direct(const uint8_t* blk, const void* exc_val, const uint16_t* ep, uint4 ma, uint4 mb, PT* out_vec,
+                                                  int t) {
 	using UT = typename Traits<PT>::UT;
+	MetaRegs m;
+	m.a    = ma;
+	m.b    = clamp_widths<PT>(mb);
 	UT* ov = reinterpret_cast<UT*>(out_vec);
 #pragma unroll 1
 	for (int i = t; i < VEC; i += 32) {
-		ov[i] = value_bits_direct<PT>(col, m, (uint32_t)i);
+		ov[i] = value_bits_direct<PT>(blk, m, (uint32_t)i);
 	}
 	__syncwarp();
-	const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
-	const uint16_t* ep = col.exc_pos + m.exc_off();
-	const bool      rd = m.scheme() != ALPB200_SCHEME_ALP;
+	const UT*  ev = static_cast<const UT*>(exc_val);
+	const bool rd = m.scheme() != ALPB200_SCHEME_ALP;
 #pragma unroll 1
 	for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
 		const uint32_t p = ep[i] & (VEC - 1);
 		UT             v = ev[i];
 		if (rd) {  // the true left part replaces the dictionary entry (rd.hpp:172-177)
-			const UT right = field_at_global<UT>(reinterpret_cast<const UT*>(col.packed + (uint64_t)m.packed_off() * 128u), p % Traits<PT>::LANES,
-			                                     (p / Traits<PT>::LANES) * m.bw(), m.bw());
+			const UT right = field_at_global<UT>(reinterpret_cast<const UT*>(blk), p % Traits<PT>::LANES, (p / Traits<PT>::LANES) * m.bw(), m.bw());
 			v              = (UT)(((v & 0xFFFFu) << m.bw()) | right);
 		}
 		ov[p] = v;
@@ -368,10 +367,10 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
         }
 	};
 
-	MetaRegs cur = sanitize_meta<PT>(load_meta(meta + v), col);
+	MetaRegs cur = clamp_meta(load_meta(meta + v));
 	bool     has_next = v_next < n_vectors;
 	MetaRegs nxt      = cur;
-	if (has_next) { nxt = sanitize_meta<PT>(load_meta(meta + v_next), col); }
+	if (has_next) { nxt = clamp_meta(load_meta(meta + v_next)); }
 	issue(cur, 0);
 	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
 	uint32_t    phase = 0;  // bit s: parity the next wait on stage s must see
@@ -385,7 +384,7 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
 		MetaRegs       nn     = nxt;
-		if (has_nn) { nn = sanitize_meta<PT>(load_meta(meta + v_nn), col); }
+		if (has_nn) { nn = clamp_meta(load_meta(meta + v_nn)); }
 
 		const uint8_t* stg = stage + (size_t)s * stage_bytes;
 		if (staged(cur)) {
@@ -400,7 +399,9 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 			out_vec = tile;
 		}
 		if (cur.block_bytes() > stage_cap) {
-			decode_vector_direct<PT>(col, cur, out_vec, t);  // the block outgrows the stage (stale hint): slow, correct
+			// the block outgrows the stage (stale hint): slow, correct
+			decode_vector_direct<PT>(col.packed + (uint64_t)cur.packed_off() * 128u, static_cast<const UT*>(col.exc_val) + cur.exc_off(),
+			                         col.exc_pos + cur.exc_off(), cur.a, cur.b, out_vec, t);
 		} else if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			decode_alp_vector(stg, cur, out_vec, t);
 			__syncwarp();  // orders the patch stores after the lane-interleaved main stores
@@ -429,6 +430,34 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 	if constexpr (OUT_TILE) {
 		if (t == 0) { bulk_wait_all(); }  // the last store must be complete before the tile's CTA goes away
 	}
+}
+
+// ---- column validation on the device (alpb200_column_validate_device) ------------------------------------------------
+// One thread per record: scheme / widths / exponent / factor / exception count in range, block and exception run inside
+// the arrays, every exception position inside the vector.  result[0] |= 1 when a record fails; result[1] = widest block.
+static __global__ void validate_kernel(ColView col, uint64_t n_vectors, uint64_t packed_capacity, uint64_t exc_capacity, uint32_t value_bytes,
+                                unsigned long long* __restrict__ result) {
+	const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n_vectors) { return; }
+	const MetaRegs m       = load_meta(col.meta + v);
+	const uint32_t T       = 8u * value_bytes, max_exp = value_bytes == 8 ? 18u : 10u;
+	const bool     rd      = m.scheme() == ALPB200_SCHEME_ALP_RD;
+	bool           ok      = m.exc_cnt() <= VEC && (rd || m.scheme() == ALPB200_SCHEME_ALP);
+	if (rd) {
+		ok = ok && m.bw() < T && m.bw() + 16u >= T && m.e() >= 1 && m.e() <= 3 && m.f() >= 1 && m.f() <= ALPB200_RD_DICT_SIZE;
+	} else {
+		ok = ok && m.bw() <= T && m.e() <= max_exp && m.f() <= m.e();
+	}
+	const uint64_t bytes = m.block_bytes();
+	ok = ok && (uint64_t)m.packed_off() * 128ull + bytes <= packed_capacity && (uint64_t)m.exc_off() + m.exc_cnt() <= exc_capacity;
+	if (ok) {
+		const uint16_t* ep = col.exc_pos + m.exc_off();
+		for (uint32_t i = 0; i < m.exc_cnt(); i++) {
+			ok = ok && ep[i] < VEC;
+		}
+	}
+	if (!ok) { atomicOr(&result[0], 1ull); }
+	if (ok) { atomicMax(&result[1], (unsigned long long)bytes); }
 }
 
 }  // namespace alpb200

@@ -60,6 +60,8 @@ int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, v
 template <typename PT>
 int launch_pad_tail(PT* d_values, uint64_t n_values, uint64_t n_padded, void* stream);
 
+int validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_block_bytes, void* stream);
+
 size_t encode_workspace_bytes(uint64_t n_vectors);
 size_t init_workspace_bytes(uint64_t n_values);
 

@@ -31,7 +31,7 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 	if (per_sm < 1) { return fail(ALPB200_ECUDA, "decode: kernel does not fit on an SM"); }
 	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
 	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
-	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos, col->packed_capacity, col->exc_capacity};
+	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
 	unsigned long long* counter = di.counters + di.next_counter;
 	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
 	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_out, stage, counter);
@@ -55,7 +55,7 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 	// The scan is bound by what the resident warps can unpack, so the block shape is the one that puts the most warps on
 	// an SM: 8 warps per block while two stages per warp are small (narrow ALP blocks), fewer when they are wide (ALP_RD on
 	// doubles: 2 x 7.3 KiB per warp would leave ONE 8-warp block per SM; 5-warp blocks fit three).
-	ColView             view {col->meta, col->packed, col->exc_val, col->exc_pos, col->packed_capacity, col->exc_capacity};
+	ColView             view {col->meta, col->packed, col->exc_val, col->exc_pos};
 	unsigned long long* counter = di.counters + di.next_counter;
 	cudaStream_t        s       = static_cast<cudaStream_t>(stream);
 	int                 best_w = 0, best_per_sm = 0;
@@ -94,6 +94,32 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 	} else {
 		TRY(launch(std::integral_constant<int, 3> {}));
 	}
+	return ALPB200_OK;
+}
+
+int validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_block_bytes, void* stream) {
+	if (!col || (value_bytes != 8 && value_bytes != 4)) { return fail(ALPB200_EINVAL, "column_validate_device: bad argument"); }
+	if (h_max_block_bytes) { *h_max_block_bytes = 0; }
+	if (col->n_vectors == 0) { return ALPB200_OK; }
+	if (!col->meta || !col->packed || !col->exc_val || !col->exc_pos) { return fail(ALPB200_EINVAL, "column_validate_device: null array"); }
+	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0 || (reinterpret_cast<uintptr_t>(col->meta) & 15u) != 0) {
+		return fail(ALPB200_EINVAL, "column_validate_device: column.packed must be 128-byte aligned, column.meta 16-byte aligned");
+	}
+	DeviceInfo di;
+	if (int rc = device_info(di)) { return rc; }
+	cudaStream_t        s      = static_cast<cudaStream_t>(stream);
+	unsigned long long* result = di.counters + di.next_counter;  // two adjacent slots of the per-device scratch (ring of 4096)
+	if (di.next_counter + 1 >= 4096) { result = di.counters; }
+	CUDA_TRY(cudaMemsetAsync(result, 0, 2 * sizeof(unsigned long long), s));
+	ColView view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	validate_kernel<<<(uint32_t)((col->n_vectors + 255) / 256), 256, 0, s>>>(view, col->n_vectors, col->packed_capacity, col->exc_capacity,
+	                                                                        (uint32_t)value_bytes, result);
+	CUDA_TRY(cudaGetLastError());
+	unsigned long long h[2] = {0, 0};
+	CUDA_TRY(cudaMemcpyAsync(h, result, sizeof(h), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(cudaStreamSynchronize(s));
+	if (h[0] != 0) { return fail(ALPB200_EINVAL, "column_validate_device: malformed vector record (field out of range, or pointing outside the column's arrays)"); }
+	if (h_max_block_bytes) { *h_max_block_bytes = h[1]; }
 	return ALPB200_OK;
 }
 

@@ -118,20 +118,22 @@ __device__ __forceinline__ double sum_rd_vector(const uint8_t* stage, const Meta
 
 // rare slow path (see decode_vector_direct): the thread's share of the vector's sum straight from global memory
 template <typename PT>
-__device__ __noinline__ double sum_vector_direct(const ColView& col, const MetaRegs& m, int t) {
-	using UT   = typename Traits<PT>::UT;
+__device__ __noinline__ double sum_vector_direct(const uint8_t* blk, const void* exc_val, const uint16_t* ep, uint4 ma, uint4 mb, int t) {
+	using UT = typename Traits<PT>::UT;
+	MetaRegs m;
+	m.a        = ma;
+	m.b        = clamp_widths<PT>(mb);
 	double acc = 0.0;
 #pragma unroll 1
 	for (int i = t; i < VEC; i += 32) {
-		acc += (double)Traits<PT>::from_bits(value_bits_direct<PT>(col, m, (uint32_t)i));
+		acc += (double)Traits<PT>::from_bits(value_bits_direct<PT>(blk, m, (uint32_t)i));
 	}
-	const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
-	const uint16_t* ep = col.exc_pos + m.exc_off();
-	const bool      rd = m.scheme() != ALPB200_SCHEME_ALP;
+	const UT*  ev = static_cast<const UT*>(exc_val);
+	const bool rd = m.scheme() != ALPB200_SCHEME_ALP;
 #pragma unroll 1
 	for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
 		const uint32_t p    = ep[i] & (VEC - 1);
-		const UT       fill = value_bits_direct<PT>(col, m, p);
+		const UT       fill = value_bits_direct<PT>(blk, m, p);
 		UT             v    = ev[i];
 		if (rd) { v = (UT)(((v & 0xFFFFu) << m.bw()) | (fill & low_mask<UT>((int)m.bw()))); }
 		acc += (double)Traits<PT>::from_bits(v) - (double)Traits<PT>::from_bits(fill);
@@ -186,10 +188,10 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
             bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
         }
 	};
-	MetaRegs cur = sanitize_meta<PT>(load_meta(meta + v), col);
+	MetaRegs cur = clamp_meta(load_meta(meta + v));
 	bool     has_next = v_next < n_vectors;
 	MetaRegs nxt      = cur;
-	if (has_next) { nxt = sanitize_meta<PT>(load_meta(meta + v_next), col); }
+	if (has_next) { nxt = clamp_meta(load_meta(meta + v_next)); }
 	issue(cur, 0);
 	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
 	uint32_t    phase = 0;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
 		MetaRegs       nn     = nxt;
-		if (has_nn) { nn = sanitize_meta<PT>(load_meta(meta + v_nn), col); }
+		if (has_nn) { nn = clamp_meta(load_meta(meta + v_nn)); }
 		const uint8_t* stg = stage + (size_t)s * stage_bytes;
 		if (staged(cur)) {
 			mbar_wait(&bars[s], (phase >> s) & 1u);
@@ -214,7 +216,9 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 		const UT*       ev  = static_cast<const UT*>(col.exc_val) + cur.exc_off();
 		const uint16_t* ep  = col.exc_pos + cur.exc_off();
 		if (cur.block_bytes() > stage_cap) {
-			acc += sum_vector_direct<PT>(col, cur, t);  // the block outgrows the stage (stale hint): slow, correct
+			// the block outgrows the stage (stale hint): slow, correct
+			acc += sum_vector_direct<PT>(col.packed + (uint64_t)cur.packed_off() * 128u, static_cast<const UT*>(col.exc_val) + cur.exc_off(),
+			                             col.exc_pos + cur.exc_off(), cur.a, cur.b, t);
 		} else if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			acc += sum_alp_vector(stg, cur, t, PT());
 			for (uint32_t i = t; i < cnt; i += 32) {  // exception: + true value - decoded fill value

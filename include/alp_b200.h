@@ -190,6 +190,15 @@ int alpb200_decode_f64(const alpb200_column* col, uint64_t first_vector, uint64_
 int alpb200_decode_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, float* d_out,
                        void* stream);
 
+/* The batched decoders assume a well-formed column (as the reference's primitives do: undefined behaviour on bad input,
+ * SURVEY.md section 8b); what they guarantee regardless is that a stale / wrong max_block_bytes hint is harmless, that at most
+ * 1024 exceptions per vector are applied and that a patch never leaves its vector.  A column of unknown provenance is
+ * checked with this call first: one pass over the records on the device (scheme, widths, exponent / factor, exception
+ * count, block and exception run inside the arrays given by packed_capacity / exc_capacity, every exception position
+ * < 1024).  Synchronises `stream`.  ALPB200_EINVAL for a malformed column; on success *h_max_block_bytes (may be NULL)
+ * receives the widest block, i.e. the decode hint. */
+int alpb200_column_validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_block_bytes, void* stream);
+
 /* Fused decode + SUM (no decoded column is written): *d_sum += sum of the decoded values of vectors
  * [first_vector, first_vector + n_vectors), accumulated in double.  The caller zeroes *d_sum.  Floating-point
  * addition order is not fixed (per-thread partial sums, one atomic add per warp).  Mirrors the reference's scan

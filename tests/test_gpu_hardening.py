@@ -82,9 +82,9 @@ def _damage(h, rng, how):
 
 
 @pytest.mark.parametrize("kind", [2, 3, 4])
-def test_damaged_columns_are_rejected_or_contained(kind):
-    """Host entry points reject a malformed column with EINVAL; the device decoders clamp whatever the records say
-    (no fault, no write outside the output, the undamaged vectors still exact)."""
+def test_damaged_columns_are_rejected(kind):
+    """A malformed column is rejected with EINVAL by the host entry points (which validate before they launch anything) and by
+    alpb200_column_validate_device for device columns; nothing is decoded, nothing faults, and the codec keeps working."""
     import torch
 
     import alp_b200
@@ -96,11 +96,12 @@ def test_damaged_columns_are_rejected_or_contained(kind):
     good = alp_b200.encode(x).to_host()
     codec = alp_b200.HostCodec(n_vec, vb)
     codec.validate(good)
+    dcol = alp_b200.DeviceColumn.from_host(good, _dev()).validate()
+    assert dcol.max_block_bytes == int(good.totals[3]) > 0  # validation also renews the decode hint
     rng = np.random.default_rng(kind)
-    ibits = torch.int64 if vb == 8 else torch.int32
     for how in ("bw", "scheme", "exc_cnt", "exc_off", "packed_off", "e", "rd_left", "pos"):
         h = good.trimmed()
-        v = _damage(h, rng, how)
+        _damage(h, rng, how)
         with pytest.raises(alp_b200.AlpError) as err:
             codec.validate(h)
         assert err.value.code == _abi.EINVAL, how
@@ -108,22 +109,37 @@ def test_damaged_columns_are_rejected_or_contained(kind):
             codec.decompress(h)
         with pytest.raises(alp_b200.AlpError):
             codec.sum(h)
-        # the device path: guard cells around the output must stay untouched, other vectors exact
-        col = alp_b200.DeviceColumn.from_host(h, _dev())
-        buf = torch.full((n_vec * 1024 + 2048,), 7.0, dtype=x.dtype, device=_dev())
-        out = buf[1024 : 1024 + n_vec * 1024]
-        alp_b200.decode(col, out=out)
-        alp_b200.decode_sum(col)
-        torch.cuda.synchronize()
-        assert bool((buf[:1024] == 7.0).all()) and bool((buf[-1024:] == 7.0).all()), how
-        keep = torch.ones(n_vec, dtype=torch.bool, device=_dev())
-        keep[v] = False
-        a = out.view(ibits).reshape(n_vec, 1024)[keep]
-        b = x.view(ibits).reshape(n_vec, 1024)[keep]
-        assert torch.equal(a, b), how
+        with pytest.raises(alp_b200.AlpError) as err:
+            alp_b200.DeviceColumn.from_host(h, _dev()).validate()
+        assert err.value.code == _abi.EINVAL, how
     # the codec still works after the rejected calls
     assert codec.decompress(good).tobytes() == x.cpu().numpy().tobytes()
     codec.close()
+
+
+def test_exception_patch_never_leaves_the_vector():
+    """What the decoders guarantee even for a column nobody validated: an exception position beyond 1023 is taken mod 1024
+    and an exception count beyond 1024 is capped — guard cells around the output stay untouched."""
+    import torch
+
+    import alp_b200
+
+    n_vec = 64
+    x = alp_b200.generate(n_vec * 1024, 2, _dev())
+    h = alp_b200.encode(x).to_host()
+    has = np.nonzero(h.meta["exc_cnt"] > 0)[0]
+    for v in has[:8]:
+        h.exc_pos[int(h.meta["exc_off"][v])] = 1024 * 37 + 5  # lands on position 5 of its own vector
+    col = alp_b200.DeviceColumn.from_host(h, _dev())
+    buf = torch.full((n_vec * 1024 + 2048,), 7.0, dtype=torch.float64, device=_dev())
+    out = buf[1024 : 1024 + n_vec * 1024]
+    alp_b200.decode(col, out=out)
+    alp_b200.decode_sum(col)
+    torch.cuda.synchronize()
+    assert bool((buf[:1024] == 7.0).all()) and bool((buf[-1024:] == 7.0).all())
+    keep = torch.ones(n_vec, dtype=torch.bool, device=_dev())
+    keep[torch.from_numpy(has[:8]).to(_dev())] = False
+    assert torch.equal(out.view(torch.int64).reshape(n_vec, 1024)[keep], x.view(torch.int64).reshape(n_vec, 1024)[keep])
 
 
 def test_misaligned_buffers_are_einval():
