@@ -49,7 +49,7 @@ int device_info(DeviceInfo& out) {
 		CUDA_TRY(cudaDeviceGetAttribute(&g_dev[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 		CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&g_dev[dev].counters), N_COUNTERS * sizeof(unsigned long long)));
 	}
-	g_dev[dev].next_counter = (g_dev[dev].next_counter + 1) % N_COUNTERS;
+	g_dev[dev].next_counter = (g_dev[dev].next_counter + 2) % N_COUNTERS;  // launches take PAIRS of slots
 	out = g_dev[dev];
 	return ALPB200_OK;
 }

@@ -69,15 +69,26 @@ __device__ __forceinline__ MetaRegs load_meta(const alpb200_vec_meta* m) {
 	r.b = __ldg(p + 1);
 	return r;
 }
-// What the hot loops guarantee whatever a record says: a block larger than the warp's stage is never bulk-copied (it takes
-// decode_vector_direct instead — a stale max_block_bytes hint stays harmless), at most 1024 exceptions are applied and an
-// exception position is taken mod 1024, so a patch never leaves the vector.  Everything else about a record (bit width vs
-// lane width, exponent / factor range, offsets inside the arrays) is the business of alpb200_column_validate_host /
-// alpb200_column_validate_device: the batched decoders assume a well-formed column, as the reference's primitives do
-// (a full per-record check in this loop cost 2-14 % of the decode throughput on B200).
-__device__ __forceinline__ MetaRegs clamp_meta(MetaRegs m) {
-	m.b.z = (m.b.z & 0xFFFF0000u) | min(m.b.z & 0xFFFFu, (uint32_t)VEC);
-	return m;
+
+// ---- slow generic path ---------------------------------------------------------------------------------------------------
+// The hot loops below size each warp's shared-memory stage from the caller's hint column.max_block_bytes and bulk-copy
+// every block into it unchecked.  A hint smaller than a real block (a stale value after re-encoding into the same
+// container, a hand-filled struct) would overrun the stage — so whenever a hint is given, the launchers first run
+// hint_check_kernel over the records of the call (one 32-byte record per thread, ~7 us per 2^20 vectors, which also pulls
+// the records into L2); if any block outgrows the stage, every thread block of the main kernel takes decode_slow /
+// sum_slow instead of its hot loop: straight from global memory, run-time widths, correct for any well-formed column.
+// The hot loops themselves stay exactly as they were (the f32 instances lose 3-14 % to any per-vector check).
+static __global__ void hint_check_kernel(const alpb200_vec_meta* __restrict__ meta, uint64_t n_vectors, uint32_t stage_cap,
+                                         unsigned long long* __restrict__ oversize) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	bool           big    = false;
+	for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vectors; v += stride) {
+		const uint4    b     = __ldg(reinterpret_cast<const uint4*>(meta + v) + 1);
+		const uint32_t bw    = b.z >> 24, e = b.w & 0xFFu;
+		const uint32_t bytes = 128u * (((b.z >> 16) & 0xFFu) == ALPB200_SCHEME_ALP_RD ? bw + e : bw);
+		big                  = big || bytes > stage_cap;
+	}
+	if (big) { *oversize = 1ull; }
 }
 
 // the bw-bit field at bit offset `bit` of lane `lane` of a T-bit-lane block in GLOBAL memory; never reads past the block
@@ -90,21 +101,9 @@ __device__ __forceinline__ UT field_at_global(const UT* blk, int lane, uint32_t 
 	if (sh + bw > TB) { v = (UT)(v | (UT)(blk[L * (w + 1) + lane] << (TB - sh))); }
 	return (UT)(v & low_mask<UT>((int)bw));
 }
-// (slow path only) widths and table indices forced into range: shifts and table reads stay defined
+// decoded bit pattern of value p of a vector, exceptions NOT applied
 template <typename PT>
-__device__ __forceinline__ uint4 clamp_widths(uint4 b) {
-	constexpr uint32_t T  = Traits<PT>::TBITS;
-	const bool         rd = ((b.z >> 16) & 0xFFu) == ALPB200_SCHEME_ALP_RD;
-	const uint32_t     bw = min(b.z >> 24, rd ? T - 1 : T);
-	const uint32_t     e  = rd ? min(max(b.w & 0xFFu, 1u), 15u) : min(b.w & 0xFFu, (uint32_t)Traits<PT>::MAX_EXP);
-	const uint32_t     f  = rd ? ((b.w >> 8) & 0xFFu) : min((b.w >> 8) & 0xFFu, e);
-	b.z = (b.z & 0x00FFFFFFu) | (bw << 24);
-	b.w = (b.w & 0xFFFF0000u) | e | (f << 8);
-	return b;
-}
-// decoded bit pattern of value p of a vector, straight from global memory, exceptions NOT applied (run-time widths)
-template <typename PT>
-__device__ __forceinline__ typename Traits<PT>::UT value_bits_direct(const uint8_t* blk, const MetaRegs& m, uint32_t p) {
+__device__ __forceinline__ typename Traits<PT>::UT value_bits_slow(const uint8_t* blk, const MetaRegs& m, uint32_t p) {
 	using T  = Traits<PT>;
 	using UT = typename T::UT;
 	using ST = typename T::ST;
@@ -116,27 +115,23 @@ __device__ __forceinline__ typename Traits<PT>::UT value_bits_direct(const uint8
 	const uint32_t idx = field_at_global<uint16_t>(reinterpret_cast<const uint16_t*>(blk + 128u * m.bw()), p & 63, (p >> 6) * m.e(), m.e());
 	return (UT)(((UT)dict_lookup(m.a, idx) << m.bw()) | d);
 }
-// Rare slow path: the vector's block does not fit the warp's stage (a stale max_block_bytes hint): decode + patch straight
-// from global memory.  Small code on purpose (one loop, run-time widths), and every argument travels BY VALUE: a reference
-// to the caller's record would force it out of registers in the hot loop.
+// one warp decodes + patches vector v straight from global memory
 template <typename PT>
-__device__ __noinline__ void decode_vector_direct(const uint8_t* blk, const void* exc_val, const uint16_t* ep, uint4 ma, uint4 mb, PT* out_vec,
-                                                  int t) {
-	using UT = typename Traits<PT>::UT;
-	MetaRegs m;
-	m.a    = ma;
-	m.b    = clamp_widths<PT>(mb);
-	UT* ov = reinterpret_cast<UT*>(out_vec);
+__device__ __forceinline__ void decode_vector_slow(const ColView& col, const MetaRegs& m, PT* out_vec, int t) {
+	using UT           = typename Traits<PT>::UT;
+	const uint8_t* blk = col.packed + (uint64_t)m.packed_off() * 128u;
+	UT*            ov  = reinterpret_cast<UT*>(out_vec);
 #pragma unroll 1
 	for (int i = t; i < VEC; i += 32) {
-		ov[i] = value_bits_direct<PT>(blk, m, (uint32_t)i);
+		ov[i] = value_bits_slow<PT>(blk, m, (uint32_t)i);
 	}
 	__syncwarp();
-	const UT*  ev = static_cast<const UT*>(exc_val);
-	const bool rd = m.scheme() != ALPB200_SCHEME_ALP;
+	const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
+	const uint16_t* ep = col.exc_pos + m.exc_off();
+	const bool      rd = m.scheme() != ALPB200_SCHEME_ALP;
 #pragma unroll 1
 	for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
-		const uint32_t p = ep[i] & (VEC - 1);
+		const uint32_t p = ep[i];
 		UT             v = ev[i];
 		if (rd) {  // the true left part replaces the dictionary entry (rd.hpp:172-177)
 			const UT right = field_at_global<UT>(reinterpret_cast<const UT*>(blk), p % Traits<PT>::LANES, (p / Traits<PT>::LANES) * m.bw(), m.bw());
@@ -144,6 +139,7 @@ __device__ __noinline__ void decode_vector_direct(const uint8_t* blk, const void
 		}
 		ov[p] = v;
 	}
+	__syncwarp();
 }
 
 // ---- ALP, 64-bit lanes -------------------------------------------------------------------------------------------
@@ -191,7 +187,7 @@ __device__ __forceinline__ ExcRegs<UT> load_exceptions(const ColView& col, const
 	x.pos = 0;
 	x.val = 0;
 	if ((uint32_t)t < m.exc_cnt()) {
-		x.pos = __ldg(col.exc_pos + m.exc_off() + t) & (VEC - 1);  // (a damaged position must not leave the vector)
+		x.pos = __ldg(col.exc_pos + m.exc_off() + t);
 		x.val = __ldg(static_cast<const UT*>(col.exc_val) + m.exc_off() + t);
 	}
 	return x;
@@ -224,14 +220,14 @@ __device__ __forceinline__ void patch_alp(const ColView& col, const MetaRegs& m,
 		const uint16_t* ep = col.exc_pos + m.exc_off();
 		for (uint32_t i = t + 32; i < cnt; i += 96) {  // three independent (position, value) loads in flight per lane
 			const uint32_t i1 = i + 32, i2 = i + 64;
-			uint32_t       p0 = ep[i] & (VEC - 1), p1 = 0, p2 = 0;
+			uint32_t       p0 = ep[i], p1 = 0, p2 = 0;
 			UT             v0 = ev[i], v1 = 0, v2 = 0;
 			if (i1 < cnt) {
-				p1 = ep[i1] & (VEC - 1);
+				p1 = ep[i1];
 				v1 = ev[i1];
 			}
 			if (i2 < cnt) {
-				p2 = ep[i2] & (VEC - 1);
+				p2 = ep[i2];
 				v2 = ev[i2];
 			}
 			ov[p0] = v0;
@@ -299,7 +295,7 @@ __device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const Col
 		const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
 		const uint16_t* ep = col.exc_pos + m.exc_off();
 		for (uint32_t i = t + 32; i < cnt; i += 32) {
-			const uint32_t p = ep[i] & (VEC - 1);
+			const uint32_t p = ep[i];
 			ov[p]            = ((ev[i] & 0xFFFFu) << rbw) | rd_right_at(stage, rbw, p, UT());
 		}
 	}
@@ -316,10 +312,18 @@ __device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const Col
 template <typename PT, int WARPS, bool OUT_TILE>
 __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
                                                                PT* __restrict__ out, uint32_t stage_bytes,
-                                                               unsigned long long* __restrict__ counter) {
+                                                               unsigned long long* __restrict__ counter,
+                                                               const unsigned long long* __restrict__ oversize) {
 	using UT = typename Traits<PT>::UT;
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	if (oversize != nullptr && *oversize != 0) {  // the hint was too small for this call (see hint_check_kernel): slow, correct
+		const uint64_t n_warps = (uint64_t)gridDim.x * WARPS;
+		for (uint64_t w = (uint64_t)blockIdx.x * WARPS + warp; w < n_vectors; w += n_warps) {
+			decode_vector_slow<PT>(col, load_meta(col.meta + first_vector + w), out + w * (uint64_t)VEC, t);
+		}
+		return;
+	}
 	// per warp: [decoded vector tile (OUT_TILE) | packed stage 0 | packed stage 1]
 	constexpr uint32_t TILE  = OUT_TILE ? VEC * sizeof(PT) : 0;
 	uint8_t*           mine  = smem + (size_t)warp * (TILE + 2 * stage_bytes);
@@ -357,20 +361,18 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 	if (v >= n_vectors) { return; }
 	const alpb200_vec_meta* meta = col.meta + first_vector;
 
-	const uint32_t stage_cap = stage_bytes - STAGE_PAD;  // the largest block a stage can take
-	auto           staged    = [&](const MetaRegs& m) { return m.block_bytes() != 0 && m.block_bytes() <= stage_cap; };
-	auto           issue     = [&](const MetaRegs& m, int s) {
-        const uint32_t bytes = m.block_bytes();
-        if (t == 0 && staged(m)) {
-            mbar_arrive_expect_tx(&bars[s], bytes);
-            bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
-        }
+	auto issue = [&](const MetaRegs& m, int s) {
+		const uint32_t bytes = m.block_bytes();
+		if (t == 0 && bytes != 0) {
+			mbar_arrive_expect_tx(&bars[s], bytes);
+			bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
+		}
 	};
 
-	MetaRegs cur = clamp_meta(load_meta(meta + v));
+	MetaRegs cur = load_meta(meta + v);
 	bool     has_next = v_next < n_vectors;
 	MetaRegs nxt      = cur;
-	if (has_next) { nxt = clamp_meta(load_meta(meta + v_next)); }
+	if (has_next) { nxt = load_meta(meta + v_next); }
 	issue(cur, 0);
 	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
 	uint32_t    phase = 0;  // bit s: parity the next wait on stage s must see
@@ -384,10 +386,10 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
 		MetaRegs       nn     = nxt;
-		if (has_nn) { nn = clamp_meta(load_meta(meta + v_nn)); }
+		if (has_nn) { nn = load_meta(meta + v_nn); }
 
 		const uint8_t* stg = stage + (size_t)s * stage_bytes;
-		if (staged(cur)) {
+		if (cur.block_bytes() != 0) {
 			mbar_wait(&bars[s], (phase >> s) & 1u);
 			phase ^= 1u << s;
 		}
@@ -398,11 +400,7 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 			__syncwarp();
 			out_vec = tile;
 		}
-		if (cur.block_bytes() > stage_cap) {
-			// the block outgrows the stage (stale hint): slow, correct
-			decode_vector_direct<PT>(col.packed + (uint64_t)cur.packed_off() * 128u, static_cast<const UT*>(col.exc_val) + cur.exc_off(),
-			                         col.exc_pos + cur.exc_off(), cur.a, cur.b, out_vec, t);
-		} else if (cur.scheme() == ALPB200_SCHEME_ALP) {
+		if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			decode_alp_vector(stg, cur, out_vec, t);
 			__syncwarp();  // orders the patch stores after the lane-interleaved main stores
 			patch_alp<PT>(col, cur, xcur, out_vec, t);
@@ -436,13 +434,13 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 // One thread per record: scheme / widths / exponent / factor / exception count in range, block and exception run inside
 // the arrays, every exception position inside the vector.  result[0] |= 1 when a record fails; result[1] = widest block.
 static __global__ void validate_kernel(ColView col, uint64_t n_vectors, uint64_t packed_capacity, uint64_t exc_capacity, uint32_t value_bytes,
-                                unsigned long long* __restrict__ result) {
+                                       unsigned long long* __restrict__ result) {
 	const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (v >= n_vectors) { return; }
-	const MetaRegs m       = load_meta(col.meta + v);
-	const uint32_t T       = 8u * value_bytes, max_exp = value_bytes == 8 ? 18u : 10u;
-	const bool     rd      = m.scheme() == ALPB200_SCHEME_ALP_RD;
-	bool           ok      = m.exc_cnt() <= VEC && (rd || m.scheme() == ALPB200_SCHEME_ALP);
+	const MetaRegs m  = load_meta(col.meta + v);
+	const uint32_t T  = 8u * value_bytes, max_exp = value_bytes == 8 ? 18u : 10u;
+	const bool     rd = m.scheme() == ALPB200_SCHEME_ALP_RD;
+	bool           ok = m.exc_cnt() <= VEC && (rd || m.scheme() == ALPB200_SCHEME_ALP);
 	if (rd) {
 		ok = ok && m.bw() < T && m.bw() + 16u >= T && m.e() >= 1 && m.e() <= 3 && m.f() >= 1 && m.f() <= ALPB200_RD_DICT_SIZE;
 	} else {

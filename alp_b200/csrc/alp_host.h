@@ -31,8 +31,9 @@ constexpr int ENC_MIN_WARPS = 8;  // fewest vectors per encode thread block (Enc
 struct DeviceInfo {
 	int sms        = 0;
 	int smem_optin = 0;
-	// work-distribution counters of the decode kernels: one slot per launch, handed out round-robin, zeroed on the
-	// launch's stream right before the kernel (allocated once per device; nothing on the hot path)
+	// scratch words of the decode kernels (work-distribution counter + "block outgrows the stage" flag): one PAIR of slots
+	// per launch, handed out round-robin, zeroed on the launch's stream right before the kernel (allocated once per device;
+	// nothing on the hot path)
 	unsigned long long* counters     = nullptr;
 	uint32_t            next_counter = 0;
 };

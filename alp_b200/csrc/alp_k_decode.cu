@@ -32,9 +32,16 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 	const uint64_t want = (n + DEC_WARPS - 1) / DEC_WARPS;
 	const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * per_sm);
 	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
-	unsigned long long* counter = di.counters + di.next_counter;
-	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
-	kern<<<grid, DEC_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(view, first, n, d_out, stage, counter);
+	cudaStream_t        s        = static_cast<cudaStream_t>(stream);
+	unsigned long long* counter  = di.counters + di.next_counter;  // [0] work counter, [1] "a block outgrows the stage"
+	unsigned long long* oversize = nullptr;
+	CUDA_TRY(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long), s));
+	if (block < widest) {  // a hint was given: make sure it covers this call's blocks (see hint_check_kernel)
+		oversize = counter + 1;
+		hint_check_kernel<<<(uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)di.sms * 8), 256, 0, s>>>(col->meta + first, n, stage - STAGE_PAD, oversize);
+		CUDA_TRY(cudaGetLastError());
+	}
+	kern<<<grid, DEC_WARPS * 32, smem, s>>>(view, first, n, d_out, stage, counter, oversize);
 	CUDA_TRY(cudaGetLastError());
 	return ALPB200_OK;
 }
@@ -58,6 +65,7 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 	ColView             view {col->meta, col->packed, col->exc_val, col->exc_pos};
 	unsigned long long* counter = di.counters + di.next_counter;
 	cudaStream_t        s       = static_cast<cudaStream_t>(stream);
+	unsigned long long* oversize = nullptr;
 	int                 best_w = 0, best_per_sm = 0;
 	auto consider = [&](auto Wc) -> int {
 		constexpr int W    = decltype(Wc)::value;
@@ -77,13 +85,18 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 	TRY(consider(std::integral_constant<int, 5> {}));
 	TRY(consider(std::integral_constant<int, 3> {}));
 	if (best_w == 0) { return fail(ALPB200_ECUDA, "decode_sum: kernel does not fit on an SM"); }
-	CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+	CUDA_TRY(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long), s));
+	if (block < widest) {  // a hint was given: make sure it covers this call's blocks (see hint_check_kernel)
+		oversize = counter + 1;
+		hint_check_kernel<<<(uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)di.sms * 8), 256, 0, s>>>(col->meta + first, n, stage - STAGE_PAD, oversize);
+		CUDA_TRY(cudaGetLastError());
+	}
 	auto launch = [&](auto Wc) -> int {
 		constexpr int  W    = decltype(Wc)::value;
 		const size_t   smem = (size_t)W * 2 * stage + W * 2 * sizeof(uint64_t);
 		const uint64_t want = (n + W - 1) / W;
 		const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * best_per_sm);
-		decode_sum_kernel<PT, W><<<grid, W * 32, smem, s>>>(view, first, n, d_sum, stage, counter);
+		decode_sum_kernel<PT, W><<<grid, W * 32, smem, s>>>(view, first, n, d_sum, stage, counter, oversize);
 		CUDA_TRY(cudaGetLastError());
 		return ALPB200_OK;
 	};
@@ -108,8 +121,7 @@ int validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_
 	DeviceInfo di;
 	if (int rc = device_info(di)) { return rc; }
 	cudaStream_t        s      = static_cast<cudaStream_t>(stream);
-	unsigned long long* result = di.counters + di.next_counter;  // two adjacent slots of the per-device scratch (ring of 4096)
-	if (di.next_counter + 1 >= 4096) { result = di.counters; }
+	unsigned long long* result = di.counters + di.next_counter;  // a pair of slots of the per-device scratch ring
 	CUDA_TRY(cudaMemsetAsync(result, 0, 2 * sizeof(unsigned long long), s));
 	ColView view {col->meta, col->packed, col->exc_val, col->exc_pos};
 	validate_kernel<<<(uint32_t)((col->n_vectors + 255) / 256), 256, 0, s>>>(view, col->n_vectors, col->packed_capacity, col->exc_capacity,

@@ -116,24 +116,23 @@ __device__ __forceinline__ double sum_rd_vector(const uint8_t* stage, const Meta
 	return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
-// rare slow path (see decode_vector_direct): the thread's share of the vector's sum straight from global memory
+// the thread's share of a vector's sum straight from global memory (slow generic path, see hint_check_kernel)
 template <typename PT>
-__device__ __noinline__ double sum_vector_direct(const uint8_t* blk, const void* exc_val, const uint16_t* ep, uint4 ma, uint4 mb, int t) {
-	using UT = typename Traits<PT>::UT;
-	MetaRegs m;
-	m.a        = ma;
-	m.b        = clamp_widths<PT>(mb);
-	double acc = 0.0;
+__device__ __forceinline__ double sum_vector_slow(const ColView& col, const MetaRegs& m, int t) {
+	using UT           = typename Traits<PT>::UT;
+	const uint8_t* blk = col.packed + (uint64_t)m.packed_off() * 128u;
+	double         acc = 0.0;
 #pragma unroll 1
 	for (int i = t; i < VEC; i += 32) {
-		acc += (double)Traits<PT>::from_bits(value_bits_direct<PT>(blk, m, (uint32_t)i));
+		acc += (double)Traits<PT>::from_bits(value_bits_slow<PT>(blk, m, (uint32_t)i));
 	}
-	const UT*  ev = static_cast<const UT*>(exc_val);
-	const bool rd = m.scheme() != ALPB200_SCHEME_ALP;
+	const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
+	const uint16_t* ep = col.exc_pos + m.exc_off();
+	const bool      rd = m.scheme() != ALPB200_SCHEME_ALP;
 #pragma unroll 1
 	for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
-		const uint32_t p    = ep[i] & (VEC - 1);
-		const UT       fill = value_bits_direct<PT>(blk, m, p);
+		const uint32_t p    = ep[i];
+		const UT       fill = value_bits_slow<PT>(blk, m, p);
 		UT             v    = ev[i];
 		if (rd) { v = (UT)(((v & 0xFFFFu) << m.bw()) | (fill & low_mask<UT>((int)m.bw()))); }
 		acc += (double)Traits<PT>::from_bits(v) - (double)Traits<PT>::from_bits(fill);
@@ -146,10 +145,24 @@ __device__ __noinline__ double sum_vector_direct(const uint8_t* blk, const void*
 template <typename PT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
                                                                   double* __restrict__ sum, uint32_t stage_bytes,
-                                                                  unsigned long long* __restrict__ counter) {
+                                                                  unsigned long long* __restrict__ counter,
+                                                                  const unsigned long long* __restrict__ oversize) {
 	using UT = typename Traits<PT>::UT;
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	if (oversize != nullptr && *oversize != 0) {  // the hint was too small for this call (hint_check_kernel): slow, correct
+		const uint64_t n_warps = (uint64_t)gridDim.x * WARPS;
+		double         part    = 0.0;
+		for (uint64_t w = (uint64_t)blockIdx.x * WARPS + warp; w < n_vectors; w += n_warps) {
+			part += sum_vector_slow<PT>(col, load_meta(col.meta + first_vector + w), t);
+		}
+#pragma unroll
+		for (int m = 16; m > 0; m >>= 1) {
+			part += __longlong_as_double((long long)shfl_xor_i64((int64_t)__double_as_longlong(part), m));
+		}
+		if (t == 0) { atomicAdd(sum, part); }
+		return;
+	}
 	uint8_t*  stage = smem + (size_t)warp * 2 * stage_bytes;
 	uint64_t* bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * 2 * stage_bytes) + 2 * warp;
 	if (t == 0) {
@@ -179,19 +192,17 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 	uint64_t v = take(), v_next = take();
 	if (v >= n_vectors) { return; }
 	const alpb200_vec_meta* meta = col.meta + first_vector;
-	const uint32_t stage_cap = stage_bytes - STAGE_PAD;
-	auto           staged    = [&](const MetaRegs& m) { return m.block_bytes() != 0 && m.block_bytes() <= stage_cap; };
-	auto           issue     = [&](const MetaRegs& m, int s) {
-        const uint32_t bytes = m.block_bytes();
-        if (t == 0 && staged(m)) {
-            mbar_arrive_expect_tx(&bars[s], bytes);
-            bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
-        }
+	auto issue = [&](const MetaRegs& m, int s) {
+		const uint32_t bytes = m.block_bytes();
+		if (t == 0 && bytes != 0) {
+			mbar_arrive_expect_tx(&bars[s], bytes);
+			bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
+		}
 	};
-	MetaRegs cur = clamp_meta(load_meta(meta + v));
+	MetaRegs cur = load_meta(meta + v);
 	bool     has_next = v_next < n_vectors;
 	MetaRegs nxt      = cur;
-	if (has_next) { nxt = clamp_meta(load_meta(meta + v_next)); }
+	if (has_next) { nxt = load_meta(meta + v_next); }
 	issue(cur, 0);
 	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
 	uint32_t    phase = 0;
@@ -206,30 +217,26 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
 		MetaRegs       nn     = nxt;
-		if (has_nn) { nn = clamp_meta(load_meta(meta + v_nn)); }
+		if (has_nn) { nn = load_meta(meta + v_nn); }
 		const uint8_t* stg = stage + (size_t)s * stage_bytes;
-		if (staged(cur)) {
+		if (cur.block_bytes() != 0) {
 			mbar_wait(&bars[s], (phase >> s) & 1u);
 			phase ^= 1u << s;
 		}
 		const uint32_t  cnt = cur.exc_cnt();
 		const UT*       ev  = static_cast<const UT*>(col.exc_val) + cur.exc_off();
 		const uint16_t* ep  = col.exc_pos + cur.exc_off();
-		if (cur.block_bytes() > stage_cap) {
-			// the block outgrows the stage (stale hint): slow, correct
-			acc += sum_vector_direct<PT>(col.packed + (uint64_t)cur.packed_off() * 128u, static_cast<const UT*>(col.exc_val) + cur.exc_off(),
-			                             col.exc_pos + cur.exc_off(), cur.a, cur.b, t);
-		} else if (cur.scheme() == ALPB200_SCHEME_ALP) {
+		if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			acc += sum_alp_vector(stg, cur, t, PT());
 			for (uint32_t i = t; i < cnt; i += 32) {  // exception: + true value - decoded fill value
-				const uint32_t p   = i < 32 ? xcur.pos : (ep[i] & (VEC - 1));
+				const uint32_t p   = i < 32 ? xcur.pos : ep[i];
 				const UT       val = i < 32 ? xcur.val : ev[i];
 				acc += (double)Traits<PT>::from_bits(val) - alp_value_at(stg, cur, p, PT());
 			}
 		} else {
 			acc += sum_rd_vector<PT>(stg, cur, t);
 			for (uint32_t i = t; i < cnt; i += 32) {
-				const uint32_t p    = i < 32 ? xcur.pos : (ep[i] & (VEC - 1));
+				const uint32_t p    = i < 32 ? xcur.pos : ep[i];
 				const uint32_t left = (uint32_t)((i < 32 ? xcur.val : ev[i]) & 0xFFFFu);
 				acc += rd_value<PT>(stg, cur, p, true, left) - rd_value<PT>(stg, cur, p, false, 0);
 			}

@@ -191,9 +191,10 @@ int alpb200_decode_f32(const alpb200_column* col, uint64_t first_vector, uint64_
                        void* stream);
 
 /* The batched decoders assume a well-formed column (as the reference's primitives do: undefined behaviour on bad input,
- * SURVEY.md section 8b); what they guarantee regardless is that a stale / wrong max_block_bytes hint is harmless, that at most
- * 1024 exceptions per vector are applied and that a patch never leaves its vector.  A column of unknown provenance is
- * checked with this call first: one pass over the records on the device (scheme, widths, exponent / factor, exception
+ * SURVEY.md section 8b).  What they guarantee regardless: a stale / wrong max_block_bytes hint is harmless — whenever a hint is
+ * given, the records of the call are checked against it on the device first and the call falls back to a slow, generic
+ * path if a block outgrows the shared-memory stage the hint sized.  A column of unknown provenance is checked with this
+ * call first: one pass over the records on the device (scheme, widths, exponent / factor, exception
  * count, block and exception run inside the arrays given by packed_capacity / exc_capacity, every exception position
  * < 1024).  Synchronises `stream`.  ALPB200_EINVAL for a malformed column; on success *h_max_block_bytes (may be NULL)
  * receives the widest block, i.e. the decode hint. */

@@ -13,7 +13,7 @@ def timed(fn, n=10):
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 29
 dev = torch.device("cuda:0")
 print("lib", alp_b200.LIB_PATH)
-for kind in (2, 3, 4):
+for kind in [int(k) for k in os.environ.get("KINDS", "2,3,4").split(",")]:
     x = alp_b200.generate(1 << lg, kind, dev)
     col = alp_b200.encode(x); col.read_totals()
     out = torch.empty_like(x); acc = torch.zeros(1, dtype=torch.float64, device=dev)
