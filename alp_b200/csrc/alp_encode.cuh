@@ -525,8 +525,15 @@ __device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&&
 	for_each_exception<PT>(pl, myexc, t, [&](uint32_t rank, uint32_t p) { store(rank, p, value_of(p)); });
 }
 
+#ifndef ALPB200_ENC_LOOKBACK
+#define ALPB200_ENC_LOOKBACK 1  // 1: blocks resolve their prefix by look-back from the scanner's anchors; 0: per-block prefixes from the scanner
+#endif
+#ifndef ALPB200_ENC_SPIN_NS
+#define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth)
+#endif
+
 // ---- placement: in-order prefix sums over thread blocks ---------------------------------------------------------------
-// Every block publishes its aggregate (packed 128-byte units << 32 | exception slots) and then waits for its exclusive
+// Every block publishes its aggregate (packed 128-byte units << AGG_SHIFT | exception slots) and then waits for its exclusive
 // prefix.  The prefixes are produced by ONE scanner warp — the last warp of the block that drew ticket 0 turns into it
 // once its own vector is written — which walks the aggregates in ticket order, 128 per step (one 32-byte sector per
 // lane), and publishes the running sums.  The scanner advances 128 blocks per L2 round trip, several times faster than
@@ -534,8 +541,13 @@ __device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&&
 // decoupled look-back with a 32-wide window per round trip cannot keep up here: ~450 blocks are in flight and the prefix
 // frontier would advance only 32 blocks per round trip.)  Tickets are drawn when a block starts, so every predecessor
 // of a waiting block is already resident: no deadlock.
-// status word: [63] valid | [61:32] packed size in 128-byte units | [31:0] exception slots
+// status word: [63] valid | [61:33] packed size in 128-byte units | [32:0] exception slots
 constexpr uint64_t SCAN_VALID = 1ull << 63, SCAN_VAL = (1ull << 62) - 1;
+// aggregate / prefix value: packed 128-byte units << AGG_SHIFT | exception slots.  33 bits of exception slots: a call of 2^22
+// vectors whose every value is an exception (2^32 slots) must not carry into the units half; 29 bits of units cover 2^22
+// vectors at the widest block (66 units).
+constexpr int      AGG_SHIFT    = 33;
+constexpr uint64_t AGG_EXC_MASK = (1ull << AGG_SHIFT) - 1;
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
 	uint64_t v;
@@ -606,6 +618,105 @@ __device__ __forceinline__ void scan_blocks(const uint64_t* aggregates, uint64_t
 	}
 }
 
+// ---- placement, second scheme: adaptive look-back on top of ANCHORS -------------------------------------------------
+// With per-block prefixes from the scanner a waiting block sits behind three L2 hops (its last predecessor's aggregate ->
+// scanner -> prefix -> waiter): ~2.5 us per block, 20-30 % of the vector-order kernel.  Here the scanner only publishes an
+// ANCHOR every 32 blocks (the exclusive prefix of block 32 G), and a block resolves its own prefix: it takes the nearest
+// anchor that is already there — typically 3-4 groups back, the scanner's lag — and adds the aggregates from that anchor up
+// to its predecessor, which it reads itself, 32 per load, all loads in flight at once.  Only the newest few of them can
+// still be missing; each lane re-polls just its own missing entries.  The critical path shrinks to ONE hop (the last
+// predecessor's aggregate becoming visible), the scanner is off it as long as it stays within LB_DEPTH groups of the
+// frontier, and the polling traffic is ~2 KB per block once plus 8 bytes per pending entry per poll.
+// (Round 1 tried a fixed 32-block window on top of per-block prefixes — the window's start still waited for the scanner —
+// and a 128-wide window re-read in full on every poll, ~1 TB/s of L2 traffic; both lost.  The adaptive anchor is what
+// takes the scanner off the critical path, the per-entry re-poll what keeps the traffic down.)
+constexpr uint32_t LB_GROUP = 32, LB_DEPTH = 8;
+
+// run by one warp: anchors[G + 1] = exclusive prefix of block 32 (G + 1), for every complete group of 32 blocks, in order
+// (anchors[0] = the call's start offset, written by encode_prepare_kernel)
+__device__ __forceinline__ void scan_anchors(const uint64_t* aggregates, uint64_t* anchors, uint32_t n_blocks, int t, uint64_t start) {
+	uint64_t       running  = start;
+	const uint32_t n_groups = n_blocks / LB_GROUP;  // complete groups; a ragged last group needs no anchor behind it
+	uint32_t       G        = 0;
+	while (G < n_groups) {
+		uint64_t v[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			v[k] = G + k < n_groups ? ld_volatile_u64(&aggregates[(size_t)LB_GROUP * (G + k) + t]) : 0;
+		}
+		uint32_t done = 0;  // leading complete groups among the four
+		bool     run  = true;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			run = run && __all_sync(FULL, (v[k] & SCAN_VALID) != 0);
+			if (run) {
+				running += warp_sum_u64(v[k] & SCAN_VAL);
+				if (t == 0) { st_volatile_u64(&anchors[G + k + 1], SCAN_VALID | running); }
+				done++;
+			}
+		}
+		G += done;
+		if (done == 0) { __nanosleep(40); }
+	}
+}
+
+// run by one warp of a block that has published its aggregate: the exclusive prefix of block `bid`
+__device__ __forceinline__ uint64_t lookback_prefix(const uint64_t* aggregates, const uint64_t* anchors, uint32_t bid, int t) {
+	const uint32_t g = bid / LB_GROUP;
+	// the nearest anchor that is already published, at most LB_DEPTH - 1 groups back (lane j looks at anchor g - j)
+	uint64_t base = 0;
+	uint32_t G    = 0;
+	for (;;) {
+		uint64_t a = 0;
+		if ((uint32_t)t < LB_DEPTH && (uint32_t)t <= g) { a = ld_volatile_u64(&anchors[g - t]); }
+		const uint32_t ok = __ballot_sync(FULL, (a & SCAN_VALID) != 0);
+		if (ok) {
+			const int j = __ffs((int)ok) - 1;
+			base        = shfl_u64(a, j) & SCAN_VAL;
+			G           = g - (uint32_t)j;
+			break;
+		}
+		__nanosleep(ALPB200_ENC_SPIN_NS);  // the scanner is more than LB_DEPTH groups behind: wait for it
+	}
+	// aggregates of blocks [32 G, bid): chunk k = blocks 32 (G + k) .. 32 (G + k) + 31, one per lane; all loads go out at once
+	uint64_t v[LB_DEPTH];
+	bool     pending = false;
+#pragma unroll
+	for (uint32_t k = 0; k < LB_DEPTH; k++) {
+		const uint32_t i = LB_GROUP * (G + k) + (uint32_t)t;
+		v[k]             = i < bid ? ld_volatile_u64(&aggregates[i]) : SCAN_VALID;  // (beyond the predecessor: nothing to add)
+	}
+#pragma unroll
+	for (uint32_t k = 0; k < LB_DEPTH; k++) {
+		pending = pending || !(v[k] & SCAN_VALID);
+	}
+	while (__any_sync(FULL, pending)) {  // the newest predecessors are still analysing: re-poll only what is missing
+		__nanosleep(ALPB200_ENC_SPIN_NS);
+		pending = false;
+#pragma unroll
+		for (uint32_t k = 0; k < LB_DEPTH; k++) {
+			if (!(v[k] & SCAN_VALID)) {
+				v[k]    = ld_volatile_u64(&aggregates[LB_GROUP * (G + k) + (uint32_t)t]);
+				pending = pending || !(v[k] & SCAN_VALID);
+			}
+		}
+	}
+	uint64_t sum = 0;
+#pragma unroll
+	for (uint32_t k = 0; k < LB_DEPTH; k++) {
+		sum += v[k] & SCAN_VAL;
+	}
+	return base + warp_sum_u64(sum);
+}
+
+__device__ __forceinline__ void run_scanner(const uint64_t* aggregates, uint64_t* prefixes, uint32_t n_blocks, int t, uint64_t start) {
+#if ALPB200_ENC_LOOKBACK
+	scan_anchors(aggregates, prefixes, n_blocks, t, start);
+#else
+	scan_blocks(aggregates, prefixes, n_blocks, t, start);
+#endif
+}
+
 struct ColOut {
 	alpb200_vec_meta* meta;
 	uint8_t*          packed;
@@ -616,7 +727,7 @@ struct ColOut {
 	uint64_t*         totals;
 };
 
-// workspace layout: [0] ticket counter, [1] where this call's output starts (packed units << 32 | exception slots: 0, or
+// workspace layout: [0] ticket counter, [1] where this call's output starts (packed units << AGG_SHIFT | exception slots: 0, or
 // the column's running totals when appending — set by encode_prepare_kernel; completion order allocates from it with
 // atomics), [2 .. 2+n_blocks) block aggregates, [2+n_blocks .. 2+2*n_blocks) exclusive prefixes.
 //
@@ -635,9 +746,6 @@ struct ColOut {
 // ORDERED = false (alpb200_encode_unordered_*): one atomicAdd hands out the space, so blocks land in COMPLETION order:
 //                  the same blocks, the same records (offsets differ), dense, but not sorted by vector.
 //
-#ifndef ALPB200_ENC_SPIN_NS
-#define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth)
-#endif
 template <typename PT>
 struct EncodeCfg;
 template <>
@@ -658,8 +766,10 @@ struct EncodeCfg<float> {
 };
 
 // runs after the workspace was zeroed: appending calls continue at the column's running totals
-static __global__ void encode_prepare_kernel(uint64_t* workspace, const uint64_t* totals, int append) {
-	workspace[1] = append ? (((totals[0] / 128ull) << 32) | (totals[1] & 0xFFFFFFFFull)) : 0ull;
+static __global__ void encode_prepare_kernel(uint64_t* workspace, const uint64_t* totals, int append, uint32_t n_blocks) {
+	const uint64_t start    = append ? (((totals[0] / 128ull) << AGG_SHIFT) | (totals[1] & AGG_EXC_MASK)) : 0ull;
+	workspace[1]            = start;
+	workspace[2 + n_blocks] = SCAN_VALID | start;  // anchors[0] (look-back placement; the slot is prefixes[0] otherwise and rewritten)
 }
 
 template <typename PT, int WARPS, bool ORDERED>
@@ -728,9 +838,9 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	uint64_t  agg        = 0, early_excl = 0;
 	if (warp == 0) {
 		uint64_t mine_agg = 0;
-		if (t < WARPS) { mine_agg = ((uint64_t)s_units[t] << 32) | s_cnt[t]; }
+		if (t < WARPS) { mine_agg = ((uint64_t)s_units[t] << AGG_SHIFT) | s_cnt[t]; }
 		agg                 = warp_sum_u64(mine_agg);
-		const uint32_t wide = __reduce_max_sync(FULL, (uint32_t)(mine_agg >> 32));
+		const uint32_t wide = __reduce_max_sync(FULL, (uint32_t)(mine_agg >> AGG_SHIFT));
 		uint64_t       incl = mine_agg;  // offsets of the warps inside the block
 #pragma unroll
 		for (int d = 1; d < WARPS; d <<= 1) {
@@ -745,8 +855,8 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 				// completion order: one atomic hands out the block's space (its round trip overlaps the packing below);
 				// the running totals are the column totals
 				early_excl = (uint64_t)atomicAdd(reinterpret_cast<unsigned long long*>(workspace + 1), (unsigned long long)agg);
-				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[0]), (unsigned long long)(agg >> 32) * 128ull);
-				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & 0xFFFFFFFFull));
+				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[0]), (unsigned long long)(agg >> AGG_SHIFT) * 128ull);
+				atomicAdd(reinterpret_cast<unsigned long long*>(&col.totals[1]), (unsigned long long)(agg & AGG_EXC_MASK));
 			}
 			atomicMax(reinterpret_cast<unsigned long long*>(&col.totals[3]), (unsigned long long)wide * 128ull);
 		}
@@ -800,34 +910,35 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		} else if (bid == 0) {
 			if (t == 0) { excl = workspace[1]; }  // where this call's output starts (0 unless appending)
 		} else {
-			// (Blocks resolving their own prefix from a window of predecessors next to the scanner — one L2 round trip
-			// instead of three — was measured twice and lost both times: 128-wide without back-off, ~1 TB/s of polling on
-			// L2, 4.65 vs 3.9 ms; 32-wide with back-off and all 32 lanes of this warp polling, 1.66 vs 1.52 ms per 2^29.)
+#if ALPB200_ENC_LOOKBACK
+			excl = lookback_prefix(aggregates, prefixes, bid, t);  // (`prefixes` holds the anchors in this scheme)
+#else
 			if (t == 0) {
 				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { __nanosleep(ALPB200_ENC_SPIN_NS); }
 				excl &= SCAN_VAL;
 			}
+#endif
 		}
 		if (t == 0) {
 			s_excl = excl;
 			if (ORDERED && (uint64_t)(bid + 1) * WARPS >= n_vectors) {  // last block: publish the column totals
 				const uint64_t incl = excl + agg;
-				col.totals[0]       = (incl >> 32) * 128ull;
-				col.totals[1]       = incl & 0xFFFFFFFFull;
+				col.totals[0]       = (incl >> AGG_SHIFT) * 128ull;
+				col.totals[1]       = incl & AGG_EXC_MASK;
 			}
 		}
 	}
 	__syncthreads();
 	const bool scanner = ORDERED && bid == 0 && warp == WARPS - 1;  // this warp produces every block's prefix once its own work is done
 	if (!active) {
-		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t, workspace[1]); }
+		if (scanner) { run_scanner(aggregates, prefixes, gridDim.x, t, workspace[1]); }
 		return;
 	}
 	const uint64_t my_excl   = s_excl + s_pre[warp];  // both halves add without carry into each other (sizes checked below)
-	const uint64_t units_off = my_excl >> 32, exc_off = my_excl & 0xFFFFFFFFull;
+	const uint64_t units_off = my_excl >> AGG_SHIFT, exc_off = my_excl & AGG_EXC_MASK;
 	if (units_off * 128ull + bytes > col.packed_capacity || exc_off + a.cnt > col.exc_capacity) {
 		if (t == 0) { atomicExch(reinterpret_cast<unsigned long long*>(&col.totals[2]), 1ull); }
-		if (scanner) { scan_blocks(aggregates, prefixes, gridDim.x, t, workspace[1]); }
+		if (scanner) { run_scanner(aggregates, prefixes, gridDim.x, t, workspace[1]); }
 		return;
 	}
 	uint8_t* dst = col.packed + units_off * 128ull;
@@ -876,7 +987,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	}
 	if (scanner) {
 		__syncwarp();
-		scan_blocks(aggregates, prefixes, gridDim.x, t, workspace[1]);
+		run_scanner(aggregates, prefixes, gridDim.x, t, workspace[1]);
 	}
 }
 

@@ -115,11 +115,11 @@ __device__ __forceinline__ void unpack32_rows(const uint8_t* blk, int t, Consume
 
 // ---- pack: the thread's 32 rows -> BW 32-bit words ----------------------------------------------------------------
 // OR the (masked) field of row r into the word array at a compile-time position
-template <int NW, int BIT, int N>
+template <int NW, int BIT, int N, bool MASKED = true>
 __device__ __forceinline__ void window_put(uint32_t (&w)[NW], uint32_t x) {
 	constexpr int      I = BIT >> 5, S = BIT & 31;
 	constexpr uint32_t M = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u);
-	if constexpr (N < 32) { x &= M; }
+	if constexpr (N < 32 && MASKED) { x &= M; }  // !MASKED: the caller guarantees x < 2^N
 	if constexpr (S == 0) {
 		w[I] = x;  // first field of a word
 	} else {
@@ -139,8 +139,10 @@ __device__ __forceinline__ void window_put(uint32_t (&w)[NW], uint32_t x) {
 //                       (BW <= 64): immediate.  Half 1 writes element 16*(B1 + m) + lane, B1 = ceil(BW/2): below
 //                       element 512 that is a row of half 0 (deferred until after the __syncwarp()), from 512 on it is
 //                       its own row B1 + m - 32 <= m, already consumed: immediate.
+// ROW: distance between consecutive 16-element rows of the block image in dst, in 64-bit elements (16 = dense).
+// MASKED = false: produce() already yields values below 2^BW (no AND per field).
 constexpr int PACK_DIRECT = 0, PACK_INPLACE_NARROW = 1, PACK_INPLACE_WIDE = 2;
-template <int BW, int MODE = PACK_DIRECT, typename Produce>
+template <int BW, int MODE = PACK_DIRECT, int ROW = 16, bool MASKED = true, typename Produce>
 __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, Produce&& produce) {
 	static_assert(MODE != PACK_INPLACE_NARROW || BW <= 32, "narrow in-place packing keeps every word in registers");
 	uint32_t w[BW + 1] = {};  // (every word is assigned before it is read; the initialiser only tells the front end so)
@@ -151,14 +153,14 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, P
 	constexpr int B1      = (BW + 1) / 2;                                   // first element row of half 1's pairs
 	constexpr int N_PAIRS = (BW & 1) ? (BW - 1) / 2 : BW / 2;               // per half
 	constexpr int N_LATE  = MODE == PACK_INPLACE_NARROW ? N_PAIRS : (MODE == PACK_INPLACE_WIDE ? (32 - B1 > 0 ? (32 - B1 < N_PAIRS ? 32 - B1 : N_PAIRS) : 0) : 0);
-	uint64_t*     p       = dst + 16 * ((BW & 1) ? (half ? B1 : 0) : half * (BW / 2)) + lane;
+	uint64_t*     p       = dst + ROW * ((BW & 1) ? (half ? B1 : 0) : half * (BW / 2)) + lane;
 	auto store_pair = [&](auto Mc) {
 		constexpr int m = decltype(Mc)::value;
 		if constexpr ((BW & 1) == 0) {
-			p[16 * m] = (uint64_t)w[2 * m] | ((uint64_t)w[2 * m + 1] << 32);
+			p[ROW * m] = (uint64_t)w[2 * m] | ((uint64_t)w[2 * m + 1] << 32);
 		} else {
 			const uint32_t a = half ? w[2 * m + 1] : w[2 * m], b = half ? w[2 * m + 2] : w[2 * m + 1];
-			p[16 * m]        = (uint64_t)a | ((uint64_t)b << 32);
+			p[ROW * m]       = (uint64_t)a | ((uint64_t)b << 32);
 		}
 	};
 	static_for<0, 32>([&](auto R) {
@@ -166,7 +168,7 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, P
 		uint32_t      lo, hi;
 		produce(R, lo, hi);
 		if constexpr (BW <= 32) {
-			window_put<BW + 1, r * BW, BW>(w, lo);
+			window_put<BW + 1, r * BW, BW, MASKED>(w, lo);
 		} else {
 			window_put<BW + 1, r * BW, 32>(w, lo);
 			window_put<BW + 1, r * BW + 32, BW - 32>(w, hi);
@@ -197,7 +199,7 @@ __device__ __forceinline__ void pack64_rows(int lane, int half, uint64_t* dst, P
 	}
 	if constexpr (BW & 1) {
 		const uint32_t other = __shfl_xor_sync(FULL, half ? w[0] : w[BW - 1], 16);
-		if (half) { dst[16 * ((BW - 1) / 2) + lane] = (uint64_t)other | ((uint64_t)w[0] << 32); }
+		if (half) { dst[ROW * ((BW - 1) / 2) + lane] = (uint64_t)other | ((uint64_t)w[0] << 32); }
 	}
 }
 
@@ -215,6 +217,57 @@ __device__ __forceinline__ void pack32_rows(int t, uint32_t* dst, Produce&& prod
 			constexpr int i = decltype(Ic)::value;
 			dst[32 * i + t] = w[i];
 		});
+	});
+}
+
+// ---- pack into REGISTERS ---------------------------------------------------------------------------------------------
+// The pipelined encoder (alp_encode_pipe.cuh) builds a narrow block image (BW <= 32) in the thread's registers, hands its
+// shared-memory tile to the NEXT vector's bulk load and writes the image to the column once the block's offset is known.
+// fill: the thread's 32 rows -> its BW 32-bit words (w[BW] is scratch).  store: the words -> the block (dense rows).
+template <int BW, typename Produce>
+__device__ __forceinline__ void pack64_fill(uint32_t (&w)[BW + 1], Produce&& produce) {
+	static_assert(BW <= 32, "a register image holds at most 32 words per thread");
+	static_for<0, 32>([&](auto R) {
+		constexpr int r = decltype(R)::value;
+		uint32_t      lo, hi;
+		produce(R, lo, hi);
+		window_put<BW + 1, r * BW, BW>(w, lo);
+	});
+}
+// 64-bit lanes: thread (lane, half) holds stream words half*BW .. half*BW+BW-1 of its lane (see pack64_rows); a half-warp
+// stores one full 128-byte line per instruction.  dst = the block as 64-bit elements (global memory).
+template <int BW>
+__device__ __forceinline__ void pack64_store(const uint32_t (&w)[BW + 1], int lane, int half, uint64_t* __restrict__ dst) {
+	constexpr int B1      = (BW + 1) / 2;
+	constexpr int N_PAIRS = (BW & 1) ? (BW - 1) / 2 : BW / 2;
+	uint64_t*     p       = dst + 16 * ((BW & 1) ? (half ? B1 : 0) : half * (BW / 2)) + lane;
+	static_for<0, N_PAIRS>([&](auto Mc) {
+		constexpr int m = decltype(Mc)::value;
+		if constexpr ((BW & 1) == 0) {
+			p[16 * m] = (uint64_t)w[2 * m] | ((uint64_t)w[2 * m + 1] << 32);
+		} else {
+			const uint32_t a = half ? w[2 * m + 1] : w[2 * m], b = half ? w[2 * m + 2] : w[2 * m + 1];
+			p[16 * m]        = (uint64_t)a | ((uint64_t)b << 32);
+		}
+	});
+	if constexpr (BW & 1) {  // the element the two halves of a lane share
+		const uint32_t other = __shfl_xor_sync(FULL, half ? w[0] : w[BW - 1], 16);
+		if (half) { dst[16 * ((BW - 1) / 2) + lane] = (uint64_t)other | ((uint64_t)w[0] << 32); }
+	}
+}
+// 32-bit lanes: thread t holds words 0..BW-1 of lane t; every store instruction writes one full 128-byte line
+template <int BW, typename Produce>
+__device__ __forceinline__ void pack32_fill(uint32_t (&w)[BW + 1], Produce&& produce) {
+	static_for<0, 32>([&](auto R) {
+		constexpr int r = decltype(R)::value;
+		window_put<BW + 1, r * BW, BW>(w, produce(R));
+	});
+}
+template <int BW>
+__device__ __forceinline__ void pack32_store(const uint32_t (&w)[BW + 1], int t, uint32_t* __restrict__ dst) {
+	static_for<0, BW>([&](auto Ic) {
+		constexpr int i = decltype(Ic)::value;
+		dst[32 * i + t] = w[i];
 	});
 }
 

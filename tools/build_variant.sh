@@ -6,7 +6,7 @@ set -eu
 NAME=$1; shift
 UNITS=${UNITS:-"alp_k_encode_f64 alp_k_encode_f32 alp_k_encode_f64u alp_k_encode_f32u"}
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
-OBJ=$ROOT/build/obj; VOBJ=$ROOT/build/obj_$NAME
+OBJ=${ALPB200_OBJ_DIR:-/tmp/alpb200_build/obj}; VOBJ=$(dirname $OBJ)/obj_$NAME
 mkdir -p $VOBJ $ROOT/variants
 for u in $UNITS; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I$ROOT/alp_b200/csrc -I$ROOT/include "$@" -c $ROOT/alp_b200/csrc/$u.cu -o $VOBJ/$u.o &
