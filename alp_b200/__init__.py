@@ -12,8 +12,10 @@ from .codec import (  # noqa: F401
     HostCodec,
     decode,
     decode_sum,
+    decode_values,
     device_count,
     encode,
+    fill_invalid,
     generate,
     rowgroup_init,
 )
@@ -26,8 +28,10 @@ __all__ = [
     "LIB_PATH",
     "decode",
     "decode_sum",
+    "decode_values",
     "device_count",
     "encode",
+    "fill_invalid",
     "generate",
     "lib",
     "primitives",

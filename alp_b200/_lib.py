@@ -45,6 +45,10 @@ SIGNATURES = {
     "alpb200_encode_unordered_f32": ([_P, _c.c_uint64, _P, _P, _P, _P], _c.c_int),
     "alpb200_decode_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
+    "alpb200_decode_values_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P, _P], _c.c_int),
+    "alpb200_decode_values_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P, _P], _c.c_int),
+    "alpb200_fill_invalid_f64": ([_P, _c.c_uint64, _P, _P, _P], _c.c_int),
+    "alpb200_fill_invalid_f32": ([_P, _c.c_uint64, _P, _P, _P], _c.c_int),
     "alpb200_decode_sum_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_sum_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_ctx_create": ([_P, _c.c_int, _c.c_uint64, _c.c_int], _c.c_int),

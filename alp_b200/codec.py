@@ -205,6 +205,34 @@ def decode(col, first=0, n=None, out=None):
     return out
 
 
+def fill_invalid(values, n_values, validity=None, states=None):
+    """alpb200_fill_invalid_*: fillers for NULL slots (validity: uint8 CUDA tensor, Arrow bitmap, bit set = valid) and for the
+    slots behind n_values; `values` must hold ceil(n_values / 1024) * 1024 elements.  states=None: first valid value of the
+    vector (run before rowgroup_init); states given: first valid non-exception value (run between init and encode)."""
+    _require_cuda(values, "values")
+    vb = values.element_size()
+    if values.numel() < -(-n_values // _abi.VECTOR_SIZE) * _abi.VECTOR_SIZE:
+        raise ValueError("values must have room for whole vectors")
+    with torch.cuda.device(values.device):
+        fn = getattr(lib, "alpb200_fill_invalid_" + _sfx(vb))
+        check(fn(values.data_ptr(), n_values, None if validity is None else validity.data_ptr(), None if states is None else states.data_ptr(),
+                 _stream_ptr(values.device)))
+    return values
+
+
+def decode_values(col, n_values, first=0, out=None):
+    """alpb200_decode_values_*: exactly n_values values from vector `first` on (a partial last vector goes through scratch)."""
+    if out is None:
+        out = torch.empty(n_values, dtype=_FLOAT[col.value_bytes], device=col.device)
+    _require_cuda(out, "out")
+    scratch = torch.empty(_abi.VECTOR_SIZE, dtype=_FLOAT[col.value_bytes], device=col.device)
+    st = col.as_struct()
+    with torch.cuda.device(col.device):
+        fn = getattr(lib, "alpb200_decode_values_" + _sfx(col.value_bytes))
+        check(fn(ctypes.byref(st), first, n_values, out.data_ptr(), scratch.data_ptr(), _stream_ptr(col.device)))
+    return out
+
+
 def decode_sum(col, first=0, n=None, out=None):
     """Fused decode + SUM of vectors [first, first+n): adds into the 1-element float64 CUDA tensor `out` (created
     zeroed when omitted).  Nothing is written back to HBM; addition order is not fixed."""

@@ -183,11 +183,14 @@ int compress_host(alpb200_ctx* c, const PT* h_in, uint64_t n_values_in, alpb200_
 		const uint64_t v0 = (uint64_t)k * chunk_vec, v1 = std::min(n_vec, v0 + chunk_vec);
 		const uint64_t x0 = v0 * VEC, x1 = std::min(n_values_in, v1 * VEC);
 		CUDA_TRY(cudaMemcpyAsync(d_values + x0, h_in + x0, (x1 - x0) * sizeof(PT), cudaMemcpyHostToDevice, s_in));
-		if (v1 == n_vec && n_values != n_values_in) { TRY(launch_pad_tail<PT>(d_values, n_values_in, n_values, s_in)); }
+		const bool ragged = v1 == n_vec && n_values != n_values_in;  // the column's last vector is partial
+		if (ragged) { TRY(launch_fill_invalid<PT>(d_values, n_values_in, nullptr, nullptr, s_in)); }  // real values everywhere for the sampling
 		CUDA_TRY(cudaEventRecord(c->chunk_in[k], s_in));
 		CUDA_TRY(cudaStreamWaitEvent(s_enc, c->chunk_in[k], 0));
 		alpb200_rg_state* states = c->d_states + v0 / ALPB200_ROWGROUP_VECTORS;
 		TRY(launch_init<PT>(d_values + x0, (v1 - v0) * VEC, states, c->d_ws_init, s_enc));
+		// the tail's slots take the vector's first non-exception value: no exceptions, no wider block (PRIMITIVES.md:141-144)
+		if (ragged) { TRY(launch_fill_invalid<PT>(d_values, n_values_in, nullptr, c->d_states, s_enc)); }
 		alpb200_column d_col {};
 		d_col.n_vectors       = v1 - v0;
 		d_col.meta            = c->d_meta + v0;
@@ -417,6 +420,23 @@ int sum_host(alpb200_ctx* c, const alpb200_column* h_col, double* h_sum) {
 
 }  // namespace
 
+namespace {
+// decode exactly n_values values: whole vectors straight into d_out, a partial last vector through d_scratch
+template <typename PT>
+int decode_values(const alpb200_column* col, uint64_t first, uint64_t n_values, PT* d_out, PT* d_scratch, void* stream) {
+	const uint64_t n_full = n_values / VEC, n_tail = n_values % VEC;
+	if (!col) { return fail(ALPB200_EINVAL, "decode_values: null argument"); }
+	if (first + n_full + (n_tail ? 1 : 0) > col->n_vectors) { return fail(ALPB200_EINVAL, "decode_values: value range outside the column"); }
+	if (n_tail && !d_scratch) { return fail(ALPB200_EINVAL, "decode_values: a partial last vector needs d_scratch (1024 values)"); }
+	TRY(launch_decode<PT>(col, first, n_full, d_out, stream));
+	if (n_tail) {
+		TRY(launch_decode<PT>(col, first + n_full, 1, d_scratch, stream));
+		CUDA_TRY(cudaMemcpyAsync(d_out + n_full * VEC, d_scratch, n_tail * sizeof(PT), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+	}
+	return ALPB200_OK;
+}
+}  // namespace
+
 // =====================================================================================================================
 // extern "C"
 // =====================================================================================================================
@@ -582,6 +602,20 @@ int alpb200_column_validate_host(const alpb200_column* h_col, int value_bytes) {
 	if (n_out > h_col->n_vectors * VEC || n_out + VEC <= h_col->n_vectors * VEC) { return fail(ALPB200_EINVAL, "column_validate_host: n_values does not match n_vectors"); }
 	const ChunkRange cr = chunk_range(h_col->meta, 0, h_col->n_vectors, value_bytes, h_col);
 	return check_host_column(h_col, cr, "column_validate_host");
+}
+
+int alpb200_fill_invalid_f64(double* d_values, uint64_t n_values, const uint8_t* d_validity, const alpb200_rg_state* d_states, void* stream) {
+	return launch_fill_invalid<double>(d_values, n_values, d_validity, d_states, stream);
+}
+int alpb200_fill_invalid_f32(float* d_values, uint64_t n_values, const uint8_t* d_validity, const alpb200_rg_state* d_states, void* stream) {
+	return launch_fill_invalid<float>(d_values, n_values, d_validity, d_states, stream);
+}
+
+int alpb200_decode_values_f64(const alpb200_column* col, uint64_t first, uint64_t n_values, double* d_out, double* d_scratch, void* stream) {
+	return decode_values<double>(col, first, n_values, d_out, d_scratch, stream);
+}
+int alpb200_decode_values_f32(const alpb200_column* col, uint64_t first, uint64_t n_values, float* d_out, float* d_scratch, void* stream) {
+	return decode_values<float>(col, first, n_values, d_out, d_scratch, stream);
 }
 
 int alpb200_column_validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_block_bytes, void* stream) {

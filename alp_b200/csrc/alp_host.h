@@ -58,8 +58,9 @@ inline int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_s
 }
 template <typename PT>
 int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream);
+// fillers for NULL slots and for the slots behind n_values up to the next multiple of 1024 (alp_prims.cuh)
 template <typename PT>
-int launch_pad_tail(PT* d_values, uint64_t n_values, uint64_t n_padded, void* stream);
+int launch_fill_invalid(PT* d_values, uint64_t n_values, const uint8_t* d_validity, const alpb200_rg_state* d_states, void* stream);
 
 int validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_block_bytes, void* stream);
 

@@ -35,23 +35,26 @@ int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, v
 template int launch_init<double>(const double*, uint64_t, alpb200_rg_state*, void*, void*);
 template int launch_init<float>(const float*, uint64_t, alpb200_rg_state*, void*, void*);
 
-// tail vector: the values after n_values up to the next multiple of 1024 repeat the last value, which
-// keeps the vector's (e,f) choice and bit width what the real values ask for
+// tail vector + NULLs: see fill_invalid_kernel in alp_prims.cuh
 template <typename PT>
-__global__ void pad_tail_kernel(PT* __restrict__ v, uint64_t n_values, uint64_t n_padded) {
-	const PT last = v[n_values - 1];
-	for (uint64_t i = n_values + threadIdx.x; i < n_padded; i += blockDim.x) {
-		v[i] = last;
-	}
-}
-template <typename PT>
-int launch_pad_tail(PT* d_values, uint64_t n_values, uint64_t n_padded, void* stream) {
-	pad_tail_kernel<PT><<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_values, n_values, n_padded);
+int launch_fill_invalid(PT* d_values, uint64_t n_values, const uint8_t* d_validity, const alpb200_rg_state* d_states, void* stream) {
+	if (!d_values) { return fail(ALPB200_EINVAL, "fill_invalid: null argument"); }
+	if ((reinterpret_cast<uintptr_t>(d_validity) & 3u) != 0) { return fail(ALPB200_EINVAL, "fill_invalid: the validity bitmap must be 4-byte aligned"); }
+	const uint64_t n_vec = (n_values + VEC - 1) / VEC;
+	if (n_vec == 0) { return ALPB200_OK; }
+	constexpr int  W     = 4;
+	// without a bitmap only the last vector can have anything to fill
+	const uint64_t first = d_validity ? 0 : n_vec - 1;
+	if (!d_validity && n_values % VEC == 0) { return ALPB200_OK; }
+	const uint64_t count = n_vec - first;
+	fill_invalid_kernel<PT, W><<<(uint32_t)((count + W - 1) / W), W * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+	    d_values + first * VEC, n_values - first * VEC, reinterpret_cast<const uint32_t*>(d_validity), d_states ? d_states + first / ALPB200_ROWGROUP_VECTORS : nullptr,
+	    count);
 	CUDA_TRY(cudaGetLastError());
 	return ALPB200_OK;
 }
-template int launch_pad_tail<double>(double*, uint64_t, uint64_t, void*);
-template int launch_pad_tail<float>(float*, uint64_t, uint64_t, void*);
+template int launch_fill_invalid<double>(double*, uint64_t, const uint8_t*, const alpb200_rg_state*, void*);
+template int launch_fill_invalid<float>(float*, uint64_t, const uint8_t*, const alpb200_rg_state*, void*);
 
 }  // namespace alpb200
 

@@ -225,4 +225,83 @@ __global__ void __launch_bounds__(32) prim_rd_decode_kernel(typename Traits<PT>:
 	}
 }
 
+// ---- tail vector and NULLs (PRIMITIVES.md:141-144 "Last Vector Encoding") -----------------------------
+// The codec works on whole vectors of 1024 REAL values.  Slots that hold no data — NULLs, and the slots behind the
+// column's last value up to the next multiple of 1024 — are given a filler before the encoder sees them, so that they are
+// ordinary values to everybody downstream (and to the reference, fed the same buffer: byte-identical output).
+// One warp per vector; a vector without such slots costs one 128-byte read of the validity bitmap and nothing else.
+//   states == nullptr  first strategy:  the filler is the vector's first valid value (0 if it has none)
+//   states given       second strategy: the filler is the vector's first valid NON-EXCEPTION value under the (e,f) the
+//                      encoder will pick for it (ALP), or the first valid value whose left part is in the dictionary
+//                      (ALP_RD) — the slot then costs no exception and cannot widen the bit width.  Run after the first
+//                      strategy + row-group init (the sampling must already see real values everywhere).
+template <typename PT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) fill_invalid_kernel(PT* __restrict__ values, uint64_t n_values, const uint32_t* __restrict__ validity,
+                                                                  const alpb200_rg_state* __restrict__ states, uint64_t n_vectors) {
+	using T  = Traits<PT>;
+	using UT = typename T::UT;
+	using ST = typename T::ST;
+	const int      t = threadIdx.x & 31;
+	const uint64_t v = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+	if (v >= n_vectors) { return; }
+	PT* vec = values + v * (uint64_t)VEC;
+	// bit r of `ok`: this lane's slot in row r (position 32 r + t) holds a real value
+	uint32_t ok = 0;
+	for (int r = 0; r < 32; r++) {
+		const uint64_t i     = v * VEC + 32u * r + t;
+		bool           valid = i < n_values;
+		if (valid && validity != nullptr) { valid = (__ldg(validity + 32 * v + r) >> t) & 1u; }  // one word per row: broadcast
+		ok |= (uint32_t)valid << r;
+	}
+	if (__all_sync(FULL, ok == 0xFFFFFFFFu)) { return; }  // nothing to fill
+	// first position (in value order) that qualifies as the filler's source
+	auto first_position = [&](uint32_t mask) -> uint32_t {  // mask: bit r = this lane's slot of row r qualifies; 1024 = none
+		uint32_t rows = 0;  // lane r: ballot of row r
+		for (int r = 0; r < 32; r++) {
+			const uint32_t b = __ballot_sync(FULL, (mask >> r) & 1u);
+			if (t == r) { rows = b; }
+		}
+		const uint32_t have = __ballot_sync(FULL, rows != 0);
+		if (have == 0) { return 1024u; }
+		const int r0 = __ffs((int)have) - 1;
+		return 32u * r0 + (uint32_t)(__ffs((int)__shfl_sync(FULL, rows, r0)) - 1);
+	};
+	uint32_t src = 1024;
+	if (states == nullptr) {
+		src = first_position(ok);
+	} else {
+		StateRegs st = load_state(states + v / ALPB200_ROWGROUP_VECTORS);
+		uint32_t  good = 0;  // valid and not an exception
+		if (st.scheme == ALPB200_SCHEME_ALP_RD) {
+			const uint32_t rbw = st.right_bw(), ds = st.dict_size();
+			for (int r = 0; r < 32; r++) {
+				const uint32_t left = (uint32_t)(T::bits(vec[32 * r + t]) >> rbw);
+				bool           hit  = false;
+				for (uint32_t d = 0; d < ds; d++) {
+					hit = hit || dict_lookup(st.dict, d) == left;
+				}
+				good |= (uint32_t)(hit && ((ok >> r) & 1u)) << r;
+			}
+		} else {
+			int e = st.exp_of(0), f = st.fac_of(0);
+			if (st.k > 1) { choose_exponent_factor<PT>(vec[32 * t], st, e, f); }  // encoder.hpp:409-412 (samples 0, 32, ..., 992)
+			const PT ex = T::exp10(e), frf = T::frac10(f), fre = T::frac10(e);
+			const ST fa = T::fact10(f);
+			for (int r = 0; r < 32; r++) {
+				const PT   x   = vec[32 * r + t];
+				const ST   enc = encode_value<PT, false>(x, ex, frf);
+				const bool exc = T::bits(decode_value<PT>(enc, fa, fre)) != T::bits(x);  // (specials never round-trip: alp_encode.cuh)
+				good |= (uint32_t)(!exc && ((ok >> r) & 1u)) << r;
+			}
+		}
+		src = first_position(good);
+		if (src == 1024u) { return; }  // no such value: the first strategy's filler stays
+	}
+	const PT filler = src < 1024u ? vec[src] : (PT)0;
+	__syncwarp();
+	for (int r = 0; r < 32; r++) {
+		if (!((ok >> r) & 1u)) { vec[32 * r + t] = filler; }
+	}
+}
+
 }  // namespace alpb200

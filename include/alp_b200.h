@@ -143,6 +143,23 @@ int alpb200_rowgroup_init_f32(const float* d_in, uint64_t n_values, alpb200_rg_s
 /* Bytes of scratch alpb200_rowgroup_init_* needs for n_values (per-sampled-vector search results). */
 size_t alpb200_init_workspace_bytes(uint64_t n_values);
 
+/* Tail vector and NULLs (reference: prose only, PRIMITIVES.md:141-144 "Last Vector Encoding"; its drivers drop the tail,
+ * benchmarks/benchmark.cpp:191).  The codec works on whole vectors of 1024 real values; slots that hold no data get a
+ * filler on the device before the encoder sees them: the slots behind n_values up to the next multiple of 1024 (d_values
+ * must have room for them) and, with a validity bitmap (Arrow layout: bit i & 7 of byte i >> 3 set = value i is valid;
+ * 4-byte aligned; NULL = no NULLs), every NULL slot.
+ *   d_states == NULL  first strategy: the vector's first valid value (0.0 for a vector without any).  Call it BEFORE
+ *                     alpb200_rowgroup_init_*, so that the sampling only sees real values.
+ *   d_states given    second strategy: the vector's first valid NON-EXCEPTION value under the state the encoder will use —
+ *                     the slot then costs no exception and cannot widen the block.  Call it between init and encode.
+ * After it the buffer is an ordinary column of ceil(n_values / 1024) vectors for alpb200_rowgroup_init_* / alpb200_encode_*
+ * (and for the reference, which fed the same buffer produces the same bytes); alpb200_decode_values_* reads exactly n_values
+ * back.  alpb200_compress_host_* does all of this for a column's partial last vector. */
+int alpb200_fill_invalid_f64(double* d_values, uint64_t n_values, const uint8_t* d_validity, const alpb200_rg_state* d_states,
+                             void* stream);
+int alpb200_fill_invalid_f32(float* d_values, uint64_t n_values, const uint8_t* d_validity, const alpb200_rg_state* d_states,
+                             void* stream);
+
 /* Bytes of scratch alpb200_encode_* needs for n_vectors (decoupled look-back state). */
 size_t alpb200_encode_workspace_bytes(uint64_t n_vectors);
 
@@ -190,6 +207,15 @@ int alpb200_decode_f64(const alpb200_column* col, uint64_t first_vector, uint64_
 int alpb200_decode_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, float* d_out,
                        void* stream);
 
+/* Decode exactly n_values values starting at vector first_vector: whole vectors go straight to d_out (which then needs
+ * room for n_values values only), a partial last vector is decoded into d_scratch (1024 values; may be NULL when n_values is
+ * a multiple of 1024) and its first n_values % 1024 values are copied behind them.  This is how a column whose length is
+ * not a multiple of 1024 (see alpb200_fill_invalid_*) is read back without its padding. */
+int alpb200_decode_values_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_values, double* d_out, double* d_scratch,
+                              void* stream);
+int alpb200_decode_values_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_values, float* d_out, float* d_scratch,
+                              void* stream);
+
 /* The batched decoders assume a well-formed column (as the reference's primitives do: undefined behaviour on bad input,
  * SURVEY.md section 8b).  What they guarantee regardless: a stale / wrong max_block_bytes hint is harmless — whenever a hint is
  * given, the records of the call are checked against it on the device first and the call falls back to a slow, generic
@@ -234,8 +260,8 @@ void alpb200_ctx_destroy(alpb200_ctx* ctx);
 #define ALPB200_OPT_CHUNKS 2
 int  alpb200_ctx_set_option(alpb200_ctx* ctx, int option, int value);
 
-/* Compress a host column of n_values values (any length: a partial last vector is padded on the device with the
- * column's last value and n_values is recorded in the container) into a host column container whose arrays the
+/* Compress a host column of n_values values (any length: the slots of a partial last vector are filled on the device with
+ * that vector's first non-exception value, alpb200_fill_invalid_*, and n_values is recorded in the container) into a host column container whose arrays the
  * caller allocated (capacities in h_col; n_vectors >= ceil(n_values / 1024)).  H2D of the values, init, encode,
  * D2H of the compressed arrays.  h_col->totals[0..1] receive packed bytes / exception slots used. */
 int alpb200_compress_host_f64(alpb200_ctx* ctx, const double* h_in, uint64_t n_values, alpb200_column* h_col);

@@ -657,7 +657,90 @@ def test_host_codec_pads_a_partial_last_vector(n_tail, checker):
     col = codec.compress(x)
     assert col.n_vectors == n // 1024 + 1 and col.n_values == n
     assert codec.decompress(col).tobytes() == x.tobytes()
-    # the padded column is an ordinary column for everybody else: the checker decodes it, padding = the last value
+    # the padded column is an ordinary column for everybody else: the checker decodes it; the padding is ONE value of the tail
+    # vector (its first non-exception value), and it costs the vector no exception
     full = checker.decode_column(col)
-    assert full[:n].tobytes() == x.tobytes() and np.all(full[n:] == x[-1])
+    assert full[:n].tobytes() == x.tobytes()
+    pad = full[n:]
+    assert np.all(pad == pad[0]) and pad[0] in x[(n // 1024) * 1024 :]
+    tail_exc = int(col.meta["exc_cnt"][-1])
+    dense = checker.encode_column(full)
+    assert int(dense.meta["exc_cnt"][-1]) == tail_exc and col.meta["bw"][-1] == dense.meta["bw"][-1]
     codec.close()
+
+
+@pytest.mark.parametrize("kind", [2, 3, 4])
+@pytest.mark.parametrize("n_tail", [1, 777, 1023])
+def test_device_api_tail_vector(kind, n_tail, checker):
+    """SURVEY.md section 8f-4 through the DEVICE entry points: alpb200_fill_invalid_* (first strategy before the row-group
+    init, second strategy — the first non-exception value — after it), encode, alpb200_decode_values_*.  The filled buffer is
+    an ordinary column: the checker, fed the same padded values and the same row-group states, produces the same bytes."""
+    import torch
+
+    import alp_b200
+    from alp_b200 import _abi
+
+    n = 2 * 102400 + 3 * 1024 + n_tail
+    n_vec = -(-n // 1024)
+    full = alp_b200.generate(n_vec * 1024, kind, _dev())
+    want = full[:n].clone()
+    buf = full.clone()
+    buf[n:] = float("nan")  # whatever the caller's buffer holds behind its last value
+    alp_b200.fill_invalid(buf, n)
+    states = alp_b200.rowgroup_init(buf)
+    alp_b200.fill_invalid(buf, n, states=states)
+    ibits = torch.int64 if buf.element_size() == 8 else torch.int32
+    assert torch.equal(buf[:n].view(ibits), want.view(ibits))
+    pad = buf[n:]
+    assert bool((pad == pad[0]).all()) and bool((buf[(n_vec - 1) * 1024 : n] == pad[0]).any())
+    col = alp_b200.encode(buf, states)
+    got = alp_b200.decode_values(col, n)
+    assert got.numel() == n and torch.equal(got.view(ibits), want.view(ibits))
+    # the tail costs no exception beyond those of its real values, and the same bytes come out of the checker
+    h = col.to_host()
+    host = buf.cpu().numpy()
+    st = states.cpu().numpy().view(_abi.RG_STATE_DTYPE).reshape(-1)
+    last = host[(n_vec - 1) * 1024 :]
+    s_last = st[(n_vec - 1) // 100 : (n_vec - 1) // 100 + 1]
+    m = h.meta[-1]
+    if int(m["scheme"]) == _abi.SCHEME_ALP:
+        ref = checker.encode(last, s_last)
+        bw, base = checker.analyze_ffor(ref["enc"])
+        assert (ref["cnt"], ref["e"], ref["f"], bw, int(base)) == (int(m["exc_cnt"]), int(m["e"]), int(m["f"]), int(m["bw"]), int(m["base"]))
+        assert np.all(ref["pos"] < n - (n_vec - 1) * 1024)  # no exception sits in the padding
+        packed = checker.ffor(ref["enc"].view(np.uint64 if buf.element_size() == 8 else np.uint32), bw, base)
+        off = int(m["packed_off"]) * 128
+        assert h.packed[off : off + 128 * bw].tobytes() == packed.tobytes()
+    else:
+        ref = checker.rd_encode(last, s_last)
+        assert ref["cnt"] == int(m["exc_cnt"]) and np.all(ref["pos"] < n - (n_vec - 1) * 1024)
+
+
+def test_device_api_nulls():
+    """NULL slots (Arrow validity bitmap) are given fillers on the device: a column with 10 % NULLs — whatever garbage the
+    caller left in those slots — compresses like the column without them (no extra exceptions, same bit widths), and every
+    valid value comes back bit for bit."""
+    import torch
+
+    import alp_b200
+
+    n = 3 * 102400
+    clean = alp_b200.generate(n, 2, _dev())
+    g = torch.Generator(device=_dev()).manual_seed(7)
+    valid = torch.rand(n, device=_dev(), generator=g) >= 0.1
+    valid[5 * 1024 : 6 * 1024] = False  # one vector without a single valid value
+    dirty = clean.clone()
+    dirty[~valid] = float("nan")
+    bits = valid.view(-1, 8).to(torch.uint8) * (1 << torch.arange(8, device=_dev(), dtype=torch.uint8))
+    bitmap = bits.sum(dim=1).to(torch.uint8).contiguous()
+    alp_b200.fill_invalid(dirty, n, validity=bitmap)
+    assert not bool(torch.isnan(dirty).any())
+    states = alp_b200.rowgroup_init(dirty)
+    alp_b200.fill_invalid(dirty, n, validity=bitmap, states=states)
+    col = alp_b200.encode(dirty, states)
+    out = alp_b200.decode(col)
+    assert torch.equal(out.view(torch.int64)[valid], clean.view(torch.int64)[valid])
+    ref = alp_b200.encode(clean)
+    pb, ne = col.read_totals()
+    pb_ref, ne_ref = ref.read_totals()
+    assert ne <= ne_ref and pb <= pb_ref * 1.001  # the NULLs cost nothing: fewer real values can only mean fewer exceptions
