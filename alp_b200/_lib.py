@@ -72,9 +72,11 @@ SIGNATURES = {
     "alpb200_prim_ffor_u64": ([_P, _P, _c.c_uint8, _c.c_uint64], _c.c_int),
     "alpb200_prim_ffor_u32": ([_P, _P, _c.c_uint8, _c.c_uint32], _c.c_int),
     "alpb200_prim_ffor_u16": ([_P, _P, _c.c_uint8, _c.c_uint16], _c.c_int),
+    "alpb200_prim_ffor_u8": ([_P, _P, _c.c_uint8, _c.c_uint8], _c.c_int),
     "alpb200_prim_unffor_u64": ([_P, _P, _c.c_uint8, _c.c_uint64], _c.c_int),
     "alpb200_prim_unffor_u32": ([_P, _P, _c.c_uint8, _c.c_uint32], _c.c_int),
     "alpb200_prim_unffor_u16": ([_P, _P, _c.c_uint8, _c.c_uint16], _c.c_int),
+    "alpb200_prim_unffor_u8": ([_P, _P, _c.c_uint8, _c.c_uint8], _c.c_int),
     "alpb200_prim_falp_f64": ([_P, _P, _c.c_uint8, _c.c_uint64, _c.c_uint8, _c.c_uint8], _c.c_int),
     "alpb200_prim_falp_f32": ([_P, _P, _c.c_uint8, _c.c_uint32, _c.c_uint8, _c.c_uint8], _c.c_int),
     "alpb200_prim_decode_f64": ([_P, _c.c_uint8, _c.c_uint8, _P], _c.c_int),

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -23,6 +24,10 @@ using namespace alpb200;
 namespace {
 thread_local std::string g_last_error;
 }
+
+#ifndef ALPB200_ENCODE_STREAM_DEFAULT
+#define ALPB200_ENCODE_STREAM_DEFAULT 0
+#endif
 
 namespace alpb200 {
 
@@ -52,6 +57,16 @@ int device_info(DeviceInfo& out) {
 	g_dev[dev].next_counter = (g_dev[dev].next_counter + 2) % N_COUNTERS;  // launches take PAIRS of slots
 	out = g_dev[dev];
 	return ALPB200_OK;
+}
+
+bool encode_uses_stream() {
+	static const int choice = [] {
+		const char* e = getenv("ALPB200_ENCODE_KERNEL");
+		if (e && strcmp(e, "block") == 0) { return 0; }
+		if (e && strcmp(e, "stream") == 0) { return 1; }
+		return ALPB200_ENCODE_STREAM_DEFAULT;
+	}();
+	return choice != 0;
 }
 
 size_t encode_workspace_bytes(uint64_t n_vectors) {

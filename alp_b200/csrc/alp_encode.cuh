@@ -114,9 +114,12 @@ __device__ __forceinline__ void choose_exponent_factor(PT xs, const StateRegs& s
 // The analysis and packing code reads row r of the thread's 32 rows through an IO policy with a compile-time row
 // number.  TileIO works on a shared-memory copy of the vector (value order) and stores the encoded integers back in
 // place — the batched kernel's tile (filled by a bulk-async copy) and the single-vector primitives' tile alike.
-template <typename PT>
+// KEEP_EXC (the streaming encoder, alp_encode_stream.cuh): exception slots keep the ORIGINAL bits (ALP_RD: every slot does),
+// so the exceptions' values can be gathered from the tile after the analysis instead of from global memory.
+template <typename PT, bool KEEP = false>
 struct TileIO {
 	using UT = typename Traits<PT>::UT;
+	static constexpr bool KEEP_EXC = KEEP;
 	UT* tile;
 	int t;
 	__device__ __forceinline__ TileIO(UT* tile_, int lane_id) : tile(tile_), t(lane_id) {}
@@ -213,7 +216,11 @@ __device__ __forceinline__ bool analyze_rows(IO& io, int e, int f, RowAcc<PT>& a
 			const PT dec = decode_value<PT>(enc, fa, fre);                       // :347
 			exc          = T::bits(dec) != xb;
 		}
-		io.store(R, (UT)enc);
+		if constexpr (IO::KEEP_EXC) {
+			if (!exc) { io.store(R, (UT)enc); }  // (a predicated store: no extra instruction)
+		} else {
+			io.store(R, (UT)enc);
+		}
 		if (exc) { acc.myexc |= 1u << r; }
 		if (!exc) {  // exceptions take no part in min / max (predicated, no branch)
 			if constexpr (sizeof(PT) == 8) {
@@ -312,7 +319,7 @@ __device__ __forceinline__ void analyze_rd(const alpb200_rg_state* state, const 
 		constexpr int  r    = decltype(R)::value;
 		const UT       bits = io.load(R);
 		const uint32_t left = (uint32_t)(bits >> rbw);
-		io.store(R, bits & rmask);
+		if constexpr (!IO::KEEP_EXC) { io.store(R, bits & rmask); }  // (KEEP_EXC: the packer masks to right_bw bits itself)
 		uint32_t idx = ds;  // rd.hpp:129-131: a left part nobody has seen gets the smallest non-dictionary index
 		// (entries are distinct — rd.hpp:56-66 takes them from a map's keys; descending, so that the lowest slot would win)
 #pragma unroll
@@ -746,6 +753,19 @@ struct ColOut {
 // ORDERED = false (alpb200_encode_unordered_*): one atomicAdd hands out the space, so blocks land in COMPLETION order:
 //                  the same blocks, the same records (offsets differ), dense, but not sorted by vector.
 //
+// vectors (= warps) per thread block: build knobs (tools/build_variant.sh)
+#ifndef ALPB200_ENC_WARPS64
+#define ALPB200_ENC_WARPS64 9
+#endif
+#ifndef ALPB200_ENC_WARPS32
+#define ALPB200_ENC_WARPS32 8
+#endif
+#ifndef ALPB200_ENC_EXC_REGS64
+#define ALPB200_ENC_EXC_REGS64 2
+#endif
+#ifndef ALPB200_ENC_EXC_REGS32
+#define ALPB200_ENC_EXC_REGS32 4
+#endif
 template <typename PT>
 struct EncodeCfg;
 template <>
@@ -754,15 +774,17 @@ struct EncodeCfg<double> {
 	static constexpr uint32_t INPLACE_MAX   = SMEM_PER_WARP;         // largest block (bytes) packed in place: whatever fits the tile
 	// 9 warps x 3 blocks = 27 warps per SM: what 227 KiB of shared memory hold at 8 KiB a vector (72 registers per thread).
 	// Measured against 8 x 3 (80 registers): 2-3 % faster.
-	static constexpr int      WARPS         = 9;
-	static constexpr int      WARPS_PER_SM  = 27;
+	static constexpr int      EXC_REGS      = ALPB200_ENC_EXC_REGS64;  // exceptions held in registers per lane across the placement wait (x 32 per vector)
+	static constexpr int      WARPS         = ALPB200_ENC_WARPS64;
+	static constexpr int      WARPS_PER_SM  = 27 / WARPS * WARPS;
 };
 template <>
 struct EncodeCfg<float> {
 	static constexpr uint32_t SMEM_PER_WARP = 35 * 128u;  // tile (32 units); every f32 block fits: 32 bits, or ALP_RD 31 + 3
 	static constexpr uint32_t INPLACE_MAX   = SMEM_PER_WARP;
-	static constexpr int      WARPS         = 8;
-	static constexpr int      WARPS_PER_SM  = 32;  // 4.4 KiB and 64 registers
+	static constexpr int      EXC_REGS      = ALPB200_ENC_EXC_REGS32;
+	static constexpr int      WARPS         = ALPB200_ENC_WARPS32;
+	static constexpr int      WARPS_PER_SM  = 32 / WARPS * WARPS;  // 4.4 KiB and 64 registers
 };
 
 // runs after the workspace was zeroed: appending calls continue at the column's running totals
@@ -784,6 +806,8 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	__shared__ uint32_t s_units[WARPS], s_cnt[WARPS];
 	__shared__ uint64_t s_excl, s_pre[WARPS];
 	__shared__ __align__(8) uint64_t s_bar[WARPS];
+	constexpr int EXC_REGS = Cfg::EXC_REGS, EXC_CAP = 32 * EXC_REGS;
+	__shared__ uint16_t s_pos[WARPS][EXC_CAP > 0 ? EXC_CAP : 1];  // positions of a vector's first EXC_CAP exceptions, by rank
 
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
 	// ORDERED: tickets are drawn when a block starts, so every predecessor of a waiting block is resident (no deadlock)
@@ -820,7 +844,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		rd = st.scheme == ALPB200_SCHEME_ALP_RD;
 		__syncwarp();
 		mbar_wait(&s_bar[warp], 0);
-		TileIO<PT> io(tile, t);
+		TileIO<PT, true> io(tile, t);  // exception slots keep their original bits (ALP_RD: every slot)
 		if (rd) {
 			analyze_rd<PT>(state, st, t, io, a, [](int, uint32_t) {});
 		} else {
@@ -862,6 +886,37 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		}
 	}
 	const uint32_t bytes = units * 128u;
+	// ---- exceptions, first part: ranks, and the ORIGINALS of up to EXC_CAP exceptions into registers -------------------------
+	// The tile still holds the original bits at exception slots (KEEP_EXC), so the values are gathered from shared memory
+	// now — before the pack overwrites the tile and before the placement wait — instead of being re-read from global memory
+	// (one dependent L2 round trip per vector) once the output offset is known.  What remains after the wait is stores.
+	const uint32_t rbw = a.bw;
+	ExcPlan        plan;
+	plan.any     = false;
+	plan.rowmask = plan.pre = 0;
+	UT       ev_reg[EXC_REGS > 0 ? EXC_REGS : 1];
+	uint32_t ep_reg[EXC_REGS > 0 ? EXC_REGS : 1];
+	bool     captured = false;  // warp-uniform
+	if (active) {
+		plan     = plan_exceptions<PT>(a.myexc, t);
+		captured = EXC_REGS > 0 && plan.any && a.cnt <= (uint32_t)EXC_CAP;
+		if (captured) {
+			for_each_exception<PT>(plan, a.myexc, t, [&](uint32_t rank, uint32_t p) { s_pos[warp][rank] = (uint16_t)p; });
+			__syncwarp();  // positions filed; the tile is complete (analysis stored to it lane by lane)
+#pragma unroll
+			for (int k = 0; k < EXC_REGS; k++) {
+				const uint32_t i = (uint32_t)t + 32u * k;
+				ev_reg[k] = 0;
+				ep_reg[k] = 0;
+				if (i < a.cnt) {
+					const uint32_t p    = s_pos[warp][i];
+					const UT       bits = tile[p];
+					ep_reg[k]           = p;
+					ev_reg[k]           = rd ? (UT)(bits >> rbw) : bits;
+				}
+			}
+		}
+	}
 	// ---- step 4: build the packed block image in shared memory while the scanner works out this block's offsets ----
 	bool staged = false;  // warp-uniform: the block sits at `mine`, ready for a bulk store
 	// (An ALP_RD block of 63 + 3 or 62 + 3 units on doubles would outgrow the tile.  Completion order has no wait to fill:
@@ -884,18 +939,13 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	// the wait is a coalesced loop: 32 consecutive ranks per step, 32 independent loads of the original values in flight,
 	// contiguous stores.  (Walking the exceptions thread by thread with one dependent L2 load per step was what kept
 	// exception-heavy columns — 90-150 per vector — at 0.42-0.49 of the roofline.)  Otherwise the values are fetched and stored inside that walk.
-	const uint32_t rbw       = a.bw;
 	auto           exc_value = [&](uint32_t p) -> UT {
         const UT bits = T::bits(in_vec[p]);
         return rd ? (UT)(bits >> rbw) : bits;
 	};
-	ExcPlan plan;
-	plan.any     = false;
-	plan.rowmask = plan.pre = 0;
 	uint16_t* pos_list = reinterpret_cast<uint16_t*>(mine + bytes);
 	bool      listed   = false;  // warp-uniform
-	if (active) {
-		plan   = plan_exceptions<PT>(a.myexc, t);
+	if (active && !captured) {
 		listed = staged && plan.any && Cfg::SMEM_PER_WARP - bytes >= 2u * a.cnt;
 		if (listed) {
 			__syncwarp();  // every lane is done reading its rows of the tile (32-bit lanes pack without a warp-wide sync)
@@ -955,7 +1005,16 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	// ---- exceptions, in position order ----
 	UT*       ev = static_cast<UT*>(col.exc_val) + exc_off;
 	uint16_t* ep = col.exc_pos + exc_off;
-	if (listed) {
+	if (captured) {
+#pragma unroll
+		for (int k = 0; k < EXC_REGS; k++) {
+			const uint32_t i = (uint32_t)t + 32u * k;
+			if (i < a.cnt) {
+				ev[i] = ev_reg[k];
+				ep[i] = (uint16_t)ep_reg[k];
+			}
+		}
+	} else if (listed) {
 		for (uint32_t i = t; i < a.cnt; i += 32) {
 			const uint32_t p = pos_list[i];
 			ev[i]            = exc_value(p);

@@ -26,7 +26,7 @@ int fail(int code, const char* fmt, const char* a = "", const char* b = "");
 	} while (0)
 
 constexpr int DEC_WARPS = 8;
-constexpr int ENC_MIN_WARPS = 8;  // fewest vectors per encode thread block (EncodeCfg<PT>::WARPS); sizes the workspace
+constexpr int ENC_MIN_WARPS = 2;  // fewest vectors per encode thread block (EncodeCfg<PT>::WARPS); sizes the workspace
 
 struct DeviceInfo {
 	int sms        = 0;
@@ -47,6 +47,13 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 template <typename PT, bool ORDERED>
 int launch_encode_impl(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
                        bool append);
+// the streaming (persistent, warp-specialised) form of the vector-order encoder: same workspace, same bytes (alp_encode_stream.cuh)
+template <typename PT>
+int launch_encode_stream(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
+                         bool append);
+// which kernel serves alpb200_encode_* (vector order): 1 = streaming pipeline (default), 0 = one thread block per 9 / 8 vectors;
+// ALPB200_ENCODE_KERNEL=block|stream in the environment overrides it (development A/B, read once)
+bool encode_uses_stream();
 // ordered = true: blocks in vector order (alpb200_encode_*); false: completion order (alpb200_encode_unordered_*).
 // append  = true: the output continues where col->totals says the column ends (meta / d_in / d_states point at the
 //                 first vector of this call; packed / exc arrays and their offsets stay those of the whole column).

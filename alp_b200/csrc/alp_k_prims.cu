@@ -310,6 +310,28 @@ int alpb200_prim_ffor_u16(const uint16_t* h_in, uint16_t* h_out, uint8_t bw, uin
 	TRY(out.download(h_out, 128u * bw));
 	return ALPB200_OK;
 }
+int alpb200_prim_ffor_u8(const uint8_t* h_in, uint8_t* h_out, uint8_t bw, uint8_t base) {
+	if (!h_in || !h_out) { return fail(ALPB200_EINVAL, "prim_ffor: null argument"); }
+	if (bw > 8) { return fail(ALPB200_EINVAL, "prim_ffor: bit width exceeds the lane width"); }
+	DevBuf in, out;
+	TRY(in.upload(h_in, VEC));
+	TRY(out.alloc(128u * 8u));
+	prim_ffor8_kernel<<<1, 32>>>(in.as<uint8_t>(), out.as<uint8_t>(), bw, base);
+	TRY(finish_kernel());
+	TRY(out.download(h_out, 128u * bw));
+	return ALPB200_OK;
+}
+int alpb200_prim_unffor_u8(const uint8_t* h_in, uint8_t* h_out, uint8_t bw, uint8_t base) {
+	if (!h_in || !h_out) { return fail(ALPB200_EINVAL, "prim_unffor: null argument"); }
+	if (bw > 8) { return fail(ALPB200_EINVAL, "prim_unffor: bit width exceeds the lane width"); }
+	DevBuf in, out;
+	TRY(in.upload(h_in, bw ? 128u * bw : 16u));
+	TRY(out.alloc(VEC));
+	prim_unffor8_kernel<<<1, 32>>>(in.as<uint8_t>(), out.as<uint8_t>(), bw, base);
+	TRY(finish_kernel());
+	TRY(out.download(h_out, VEC));
+	return ALPB200_OK;
+}
 int alpb200_prim_unffor_u64(const uint64_t* in, uint64_t* out, uint8_t bw, uint64_t base) { return prim_unffor<double>(in, out, bw, base); }
 int alpb200_prim_unffor_u32(const uint32_t* in, uint32_t* out, uint8_t bw, uint32_t base) { return prim_unffor<float>(in, out, bw, base); }
 int alpb200_prim_unffor_u16(const uint16_t* h_in, uint16_t* h_out, uint8_t bw, uint16_t base) {

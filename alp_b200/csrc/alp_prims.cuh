@@ -113,6 +113,36 @@ __global__ void __launch_bounds__(32) prim_unffor16_kernel(const uint16_t* __res
 	}
 }
 
+// ffor / unffor on 8-bit lanes (ffor.hpp:10, unffor.hpp:10; src/fastlanes_generated_ffor.cpp:4-300): 128 lanes x 8 rows, value
+// v = 128*row + lane, stream word w of a lane at byte 128*w + lane.  A lane's whole stream is 8*bw <= 64 bits: one register.
+__global__ void __launch_bounds__(32) prim_ffor8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t bw, uint8_t base) {
+	const int t = threadIdx.x;
+	if (bw == 0) { return; }
+	const uint32_t mask = (1u << bw) - 1;  // bw <= 8
+	for (int lane = t; lane < 128; lane += 32) {
+		uint64_t acc = 0;
+		for (int row = 0; row < 8; row++) {
+			acc |= (uint64_t)(((uint32_t)(uint8_t)(in[128 * row + lane] - base)) & mask) << (row * bw);
+		}
+		for (uint32_t w = 0; w < bw; w++) {
+			out[128 * w + lane] = (uint8_t)(acc >> (8 * w));
+		}
+	}
+}
+__global__ void __launch_bounds__(32) prim_unffor8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t bw, uint8_t base) {
+	const int      t    = threadIdx.x;
+	const uint32_t mask = (1u << bw) - 1;
+	for (int lane = t; lane < 128; lane += 32) {
+		uint64_t acc = 0;
+		for (uint32_t w = 0; w < bw; w++) {
+			acc |= (uint64_t)in[128 * w + lane] << (8 * w);
+		}
+		for (int row = 0; row < 8; row++) {
+			out[128 * row + lane] = (uint8_t)(((uint32_t)(acc >> (row * bw)) & mask) + base);  // bw = 0: the base (unffor.cpp:4-22)
+		}
+	}
+}
+
 // unffor::unffor on 64- and 32-bit lanes (include/fastlanes/unffor.hpp:7-8)
 template <typename PT>
 __global__ void __launch_bounds__(32) prim_unffor_kernel(const uint8_t* __restrict__ in, typename Traits<PT>::UT* __restrict__ out,

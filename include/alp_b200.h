@@ -305,9 +305,11 @@ int alpb200_prim_analyze_ffor_i32(const int32_t* h_enc, uint8_t* bw, int32_t* ba
 int alpb200_prim_ffor_u64(const uint64_t* h_in, uint64_t* h_out, uint8_t bw, uint64_t base);
 int alpb200_prim_ffor_u32(const uint32_t* h_in, uint32_t* h_out, uint8_t bw, uint32_t base);
 int alpb200_prim_ffor_u16(const uint16_t* h_in, uint16_t* h_out, uint8_t bw, uint16_t base);
+int alpb200_prim_ffor_u8(const uint8_t* h_in, uint8_t* h_out, uint8_t bw, uint8_t base);
 int alpb200_prim_unffor_u64(const uint64_t* h_in, uint64_t* h_out, uint8_t bw, uint64_t base);
 int alpb200_prim_unffor_u32(const uint32_t* h_in, uint32_t* h_out, uint8_t bw, uint32_t base);
 int alpb200_prim_unffor_u16(const uint16_t* h_in, uint16_t* h_out, uint8_t bw, uint16_t base);
+int alpb200_prim_unffor_u8(const uint8_t* h_in, uint8_t* h_out, uint8_t bw, uint8_t base);
 /* generated::falp::fallback::scalar::falp (include/alp/falp.hpp:10-44): fused unffor + decode.
  * At bw == lane width the reference's fused kernel is wrong (src/falp.cpp:33311-33319); this entry point has the
  * unfused semantics unffor + decoder::decode for every width. */

@@ -287,6 +287,10 @@ namespace fastlanes { namespace generated { namespace ffor { namespace fallback 
 inline void ffor(const uint64_t* in, uint64_t* out, uint8_t bw, const uint64_t* a_base_p) { alp::check_(alpb200_prim_ffor_u64(in, out, bw, *a_base_p)); }
 inline void ffor(const uint32_t* in, uint32_t* out, uint8_t bw, const uint32_t* a_base_p) { alp::check_(alpb200_prim_ffor_u32(in, out, bw, *a_base_p)); }
 inline void ffor(const uint16_t* in, uint16_t* out, uint8_t bw, const uint16_t* a_base_p) { alp::check_(alpb200_prim_ffor_u16(in, out, bw, *a_base_p)); }
+inline void ffor(const uint8_t* in, uint8_t* out, uint8_t bw, const uint8_t* a_base_p) { alp::check_(alpb200_prim_ffor_u8(in, out, bw, *a_base_p)); }
+inline void ffor(const int8_t* in, int8_t* out, uint8_t bw, const int8_t* a_base_p) {
+	alp::check_(alpb200_prim_ffor_u8(reinterpret_cast<const uint8_t*>(in), reinterpret_cast<uint8_t*>(out), bw, static_cast<uint8_t>(*a_base_p)));
+}
 inline void ffor(const int64_t* in, int64_t* out, uint8_t bw, const int64_t* a_base_p) {
 	alp::check_(alpb200_prim_ffor_u64(reinterpret_cast<const uint64_t*>(in), reinterpret_cast<uint64_t*>(out), bw, static_cast<uint64_t>(*a_base_p)));
 }
@@ -303,6 +307,10 @@ namespace fastlanes { namespace generated { namespace unffor { namespace fallbac
 inline void unffor(const uint64_t* in, uint64_t* out, uint8_t bw, const uint64_t* a_base_p) { alp::check_(alpb200_prim_unffor_u64(in, out, bw, *a_base_p)); }
 inline void unffor(const uint32_t* in, uint32_t* out, uint8_t bw, const uint32_t* a_base_p) { alp::check_(alpb200_prim_unffor_u32(in, out, bw, *a_base_p)); }
 inline void unffor(const uint16_t* in, uint16_t* out, uint8_t bw, const uint16_t* a_base_p) { alp::check_(alpb200_prim_unffor_u16(in, out, bw, *a_base_p)); }
+inline void unffor(const uint8_t* in, uint8_t* out, uint8_t bw, const uint8_t* a_base_p) { alp::check_(alpb200_prim_unffor_u8(in, out, bw, *a_base_p)); }
+inline void unffor(const int8_t* in, int8_t* out, uint8_t bw, const int8_t* a_base_p) {
+	alp::check_(alpb200_prim_unffor_u8(reinterpret_cast<const uint8_t*>(in), reinterpret_cast<uint8_t*>(out), bw, static_cast<uint8_t>(*a_base_p)));
+}
 inline void unffor(const int64_t* in, int64_t* out, uint8_t bw, const int64_t* a_base_p) {
 	alp::check_(alpb200_prim_unffor_u64(reinterpret_cast<const uint64_t*>(in), reinterpret_cast<uint64_t*>(out), bw, static_cast<uint64_t>(*a_base_p)));
 }

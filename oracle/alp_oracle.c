@@ -117,6 +117,7 @@ static inline int32_t cast_x86_i32(float t) { return (t >= -2147483648.0f && t <
 DEFINE_FFOR(64, uint64_t)
 DEFINE_FFOR(32, uint32_t)
 DEFINE_FFOR(16, uint16_t)
+DEFINE_FFOR(8, uint8_t) /* include/fastlanes/ffor.hpp:10, unffor.hpp:10 (src/fastlanes_generated_ffor.cpp:4-300) */
 
 /* ---- double instance ---- */
 #define PT double

@@ -84,7 +84,7 @@ class CpuCodec:
             f.argtypes, f.restype = [ct, _c.c_uint8, _c.c_uint8], it
             f = self._fn("decode_value_" + sfx)
             f.argtypes, f.restype = [it, _c.c_uint8, _c.c_uint8], ct
-        for t, ct in ((64, _c.c_uint64), (32, _c.c_uint32), (16, _c.c_uint16)):
+        for t, ct in ((64, _c.c_uint64), (32, _c.c_uint32), (16, _c.c_uint16), (8, _c.c_uint8)):
             for name in ("ffor", "unffor"):
                 self._fn("%s_u%d" % (name, t)).argtypes = [_P, _P, _c.c_uint8, ct]
         self._fn("falp_f64").argtypes = [_P, _P, _c.c_uint8, _c.c_uint64, _c.c_uint8, _c.c_uint8]

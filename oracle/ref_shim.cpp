@@ -491,6 +491,8 @@ void alpref_analyze_ffor_i32(const int32_t* enc, uint8_t* bw, int32_t* base) {
 void alpref_ffor_u64(const uint64_t* in, uint64_t* out, uint8_t bw, uint64_t base) { ffor::ffor(in, out, bw, &base); }
 void alpref_ffor_u32(const uint32_t* in, uint32_t* out, uint8_t bw, uint32_t base) { ffor::ffor(in, out, bw, &base); }
 void alpref_ffor_u16(const uint16_t* in, uint16_t* out, uint8_t bw, uint16_t base) { ffor::ffor(in, out, bw, &base); }
+void alpref_ffor_u8(const uint8_t* in, uint8_t* out, uint8_t bw, uint8_t base) { ffor::ffor(in, out, bw, &base); }
+void alpref_unffor_u8(const uint8_t* in, uint8_t* out, uint8_t bw, uint8_t base) { unffor::unffor(in, out, bw, &base); }
 void alpref_unffor_u64(const uint64_t* in, uint64_t* out, uint8_t bw, uint64_t base) { unffor::unffor(in, out, bw, &base); }
 void alpref_unffor_u32(const uint32_t* in, uint32_t* out, uint8_t bw, uint32_t base) { unffor::unffor(in, out, bw, &base); }
 void alpref_unffor_u16(const uint16_t* in, uint16_t* out, uint8_t bw, uint16_t base) { unffor::unffor(in, out, bw, &base); }

@@ -84,13 +84,13 @@ def test_init_matches_reference_state(golden_vectors, port):
             assert _same(dec, x), c["name"]
 
 
-@pytest.mark.parametrize("tbits", [64, 32, 16])
+@pytest.mark.parametrize("tbits", [64, 32, 16, 8])
 def test_ffor_unffor_every_width(tbits, checker):
     """Every bit width of every lane width against the checker (src/fastlanes_generated_{ffor,unffor}.cpp dispatch)."""
     from alp_b200 import primitives as gpu
 
     rng = np.random.default_rng(tbits)
-    dt = {64: np.uint64, 32: np.uint32, 16: np.uint16}[tbits]
+    dt = {64: np.uint64, 32: np.uint32, 16: np.uint16, 8: np.uint8}[tbits]
     for bw in range(0, tbits + 1):
         base = int(rng.integers(0, 1 << min(tbits, 62)))
         span = (1 << bw) - 1

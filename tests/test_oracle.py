@@ -165,10 +165,10 @@ def test_value_round_trip_fuzz(reference, port):
             assert np.array([da], dtype=dt).tobytes() == np.array([db], dtype=dt).tobytes(), (vb, v, e, f)
 
 
-@pytest.mark.parametrize("tbits", [64, 32, 16])
+@pytest.mark.parametrize("tbits", [64, 32, 16, 8])
 def test_ffor_unffor_every_width_vs_reference(tbits, reference, port):
     rng = np.random.default_rng(tbits)
-    dt = {64: np.uint64, 32: np.uint32, 16: np.uint16}[tbits]
+    dt = {64: np.uint64, 32: np.uint32, 16: np.uint16, 8: np.uint8}[tbits]
     for bw in range(0, tbits + 1):
         base = int(rng.integers(0, 1 << min(tbits, 62)))
         vals = rng.integers(0, 1 << min(tbits, 63), size=1024, dtype=np.uint64).astype(dt)  # ffor masks, whatever the input
