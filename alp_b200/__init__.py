@@ -11,6 +11,7 @@ from .codec import (  # noqa: F401
     DeviceColumn,
     HostCodec,
     decode,
+    SUM_DECIMAL,
     decode_sum,
     decode_values,
     device_count,
@@ -27,6 +28,7 @@ __all__ = [
     "HostCodec",
     "LIB_PATH",
     "decode",
+    "SUM_DECIMAL",
     "decode_sum",
     "decode_values",
     "device_count",

@@ -51,6 +51,8 @@ SIGNATURES = {
     "alpb200_fill_invalid_f32": ([_P, _c.c_uint64, _P, _P, _P], _c.c_int),
     "alpb200_decode_sum_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_sum_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
+    "alpb200_decode_sum_ex_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _c.c_uint32, _P], _c.c_int),
+    "alpb200_decode_sum_ex_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _c.c_uint32, _P], _c.c_int),
     "alpb200_ctx_create": ([_P, _c.c_int, _c.c_uint64, _c.c_int], _c.c_int),
     "alpb200_ctx_create_ex": ([_P, _c.c_int, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_uint64], _c.c_int),
     "alpb200_column_validate_host": ([_P, _c.c_int], _c.c_int),
@@ -89,6 +91,8 @@ SIGNATURES = {
     "alpb200_prim_rd_decode_f32": ([_P, _P, _P, _P, _P, _c.c_uint16, _P], _c.c_int),
     "alpb200_prim_init_f64": ([_P, _c.c_uint64, _c.c_uint64, _P], _c.c_int),
     "alpb200_prim_init_f32": ([_P, _c.c_uint64, _c.c_uint64, _P], _c.c_int),
+    "alpb200_prim_rd_init_f64": ([_P, _c.c_uint64, _c.c_uint64, _P], _c.c_int),
+    "alpb200_prim_rd_init_f32": ([_P, _c.c_uint64, _c.c_uint64, _P], _c.c_int),
     "alpb200_generate_f64": ([_P, _c.c_uint64, _c.c_uint64, _c.c_uint64, _c.c_int, _P], _c.c_int),
     "alpb200_generate_f32": ([_P, _c.c_uint64, _c.c_uint64, _c.c_uint64, _c.c_int, _P], _c.c_int),
 }

@@ -233,17 +233,21 @@ def decode_values(col, n_values, first=0, out=None):
     return out
 
 
-def decode_sum(col, first=0, n=None, out=None):
+SUM_DECIMAL = 1  # ALPB200_SUM_DECIMAL
+
+
+def decode_sum(col, first=0, n=None, out=None, flags=0):
     """Fused decode + SUM of vectors [first, first+n): adds into the 1-element float64 CUDA tensor `out` (created
-    zeroed when omitted).  Nothing is written back to HBM; addition order is not fixed."""
+    zeroed when omitted).  Nothing is written back to HBM; addition order is not fixed.  flags: SUM_DECIMAL (float columns:
+    add the integers and convert once, see include/alp_b200.h)."""
     n = col.n_vectors - first if n is None else n
     if out is None:
         out = torch.zeros(1, dtype=torch.float64, device=col.device)
     _require_cuda(out, "out")
     st = col.as_struct()
     with torch.cuda.device(col.device):
-        fn = getattr(lib, "alpb200_decode_sum_" + _sfx(col.value_bytes))
-        check(fn(ctypes.byref(st), first, n, out.data_ptr(), _stream_ptr(col.device)))
+        fn = getattr(lib, "alpb200_decode_sum_ex_" + _sfx(col.value_bytes))
+        check(fn(ctypes.byref(st), first, n, out.data_ptr(), flags, _stream_ptr(col.device)))
     return out
 
 

@@ -528,6 +528,14 @@ int alpb200_decode_sum_f64(const alpb200_column* col, uint64_t first, uint64_t n
 int alpb200_decode_sum_f32(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream) {
 	return launch_decode_sum<float>(col, first, n, d_sum, stream);
 }
+int alpb200_decode_sum_ex_f64(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, uint32_t flags, void* stream) {
+	if (flags & ~(uint32_t)ALPB200_SUM_DECIMAL) { return fail(ALPB200_EINVAL, "decode_sum_ex: unknown flag"); }
+	return launch_decode_sum<double>(col, first, n, d_sum, stream, flags);
+}
+int alpb200_decode_sum_ex_f32(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, uint32_t flags, void* stream) {
+	if (flags & ~(uint32_t)ALPB200_SUM_DECIMAL) { return fail(ALPB200_EINVAL, "decode_sum_ex: unknown flag"); }
+	return launch_decode_sum<float>(col, first, n, d_sum, stream, flags);
+}
 
 int alpb200_ctx_create_ex(alpb200_ctx** out, int device, uint64_t max_vectors, int value_bytes, uint64_t packed_capacity, uint64_t exc_capacity) {
 	if (!out || max_vectors == 0 || max_vectors > (1ull << 22) || (value_bytes != 8 && value_bytes != 4)) {

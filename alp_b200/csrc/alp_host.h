@@ -43,7 +43,7 @@ int device_info(DeviceInfo& out);
 template <typename PT>
 int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_out, void* stream);
 template <typename PT>
-int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream);
+int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream, uint32_t flags = 0);
 template <typename PT, bool ORDERED>
 int launch_encode_impl(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
                        bool append);
@@ -64,7 +64,7 @@ inline int launch_encode(const PT* d_in, uint64_t n, const alpb200_rg_state* d_s
 	               : launch_encode_impl<PT, false>(d_in, n, d_states, col, ws, stream, append);
 }
 template <typename PT>
-int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream);
+int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream, bool force_rd = false);
 // fillers for NULL slots and for the slots behind n_values up to the next multiple of 1024 (alp_prims.cuh)
 template <typename PT>
 int launch_fill_invalid(PT* d_values, uint64_t n_values, const uint8_t* d_validity, const alpb200_rg_state* d_states, void* stream);

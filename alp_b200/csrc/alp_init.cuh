@@ -266,7 +266,7 @@ __device__ void rd_find_best_dictionary(const UT* s_bits, uint16_t* s_keys, int 
 template <typename PT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) init_finalize_kernel(const PT* __restrict__ in, uint64_t n_vectors, uint64_t n_rowgroups,
                                                                    const SearchResult* __restrict__ results,
-                                                                   alpb200_rg_state* __restrict__ states) {
+                                                                   alpb200_rg_state* __restrict__ states, uint32_t force_rd) {
 	using T  = Traits<PT>;
 	using UT = typename T::UT;
 	__shared__ UT       s_bits[WARPS][ALPB200_MAX_SAMPLES];
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(WARPS * 32) init_finalize_kernel(const PT* __r
 	r.size    = 0xFFFFFFFFu;
 	if (t < nsv) { r = results[rg * MAX_SAMPLED_VECS + t]; }
 	const uint32_t best_overall = __reduce_min_sync(FULL, r.size);
-	if (best_overall >= T::RD_LIMIT) {  // encoder.hpp:213-216
+	if (best_overall >= T::RD_LIMIT || force_rd) {  // encoder.hpp:213-216; forced: rd_encoder<PT>::init on any row-group (rd.hpp:180-185)
 		const int n = 32 * nsv;
 		for (int j = t; j < n; j += 32) {
 			const PT* vec   = in + (rg * ALPB200_ROWGROUP_VECTORS + (uint64_t)(j >> 5) * SAMPLE_JUMP) * VEC;

@@ -47,7 +47,7 @@ int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_o
 }
 
 template <typename PT>
-int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream) {
+int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream, uint32_t flags) {
 	if (!col || !d_sum) { return fail(ALPB200_EINVAL, "decode_sum: null argument"); }
 	if (first + n > col->n_vectors) { return fail(ALPB200_EINVAL, "decode_sum: vector range outside the column"); }
 	if (n == 0) { return ALPB200_OK; }
@@ -96,7 +96,7 @@ int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, dou
 		const size_t   smem = (size_t)W * 2 * stage + W * 2 * sizeof(uint64_t);
 		const uint64_t want = (n + W - 1) / W;
 		const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)di.sms * best_per_sm);
-		decode_sum_kernel<PT, W><<<grid, W * 32, smem, s>>>(view, first, n, d_sum, stage, counter, oversize);
+		decode_sum_kernel<PT, W><<<grid, W * 32, smem, s>>>(view, first, n, d_sum, stage, counter, oversize, flags);
 		CUDA_TRY(cudaGetLastError());
 		return ALPB200_OK;
 	};
@@ -137,7 +137,7 @@ int validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_
 
 template int launch_decode<double>(const alpb200_column*, uint64_t, uint64_t, double*, void*);
 template int launch_decode<float>(const alpb200_column*, uint64_t, uint64_t, float*, void*);
-template int launch_decode_sum<double>(const alpb200_column*, uint64_t, uint64_t, double*, void*);
-template int launch_decode_sum<float>(const alpb200_column*, uint64_t, uint64_t, double*, void*);
+template int launch_decode_sum<double>(const alpb200_column*, uint64_t, uint64_t, double*, void*, uint32_t);
+template int launch_decode_sum<float>(const alpb200_column*, uint64_t, uint64_t, double*, void*, uint32_t);
 
 }  // namespace alpb200

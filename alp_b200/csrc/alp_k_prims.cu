@@ -15,7 +15,7 @@ size_t init_workspace_bytes(uint64_t n_values) {
 }
 
 template <typename PT>
-int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream) {
+int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, void* ws, void* stream, bool force_rd) {
 	if (!d_in || !d_states || !ws) { return fail(ALPB200_EINVAL, "rowgroup_init: null argument"); }
 	if (n_values % VEC != 0) { return fail(ALPB200_EINVAL, "rowgroup_init: n_values must be a multiple of 1024"); }
 	const uint64_t n_vec = n_values / VEC;
@@ -27,13 +27,13 @@ int launch_init(const PT* d_in, uint64_t n_values, alpb200_rg_state* d_states, v
 	init_search_kernel<PT, W><<<(uint32_t)((jobs + W - 1) / W), W * 32, 0, s>>>(d_in, n_vec, n_rg, static_cast<SearchResult*>(ws));
 	CUDA_TRY(cudaGetLastError());
 	init_finalize_kernel<PT, W><<<(uint32_t)((n_rg + W - 1) / W), W * 32, 0, s>>>(d_in, n_vec, n_rg, static_cast<const SearchResult*>(ws),
-	                                                                              d_states);
+	                                                                              d_states, force_rd ? 1u : 0u);
 	CUDA_TRY(cudaGetLastError());
 	return ALPB200_OK;
 }
 
-template int launch_init<double>(const double*, uint64_t, alpb200_rg_state*, void*, void*);
-template int launch_init<float>(const float*, uint64_t, alpb200_rg_state*, void*, void*);
+template int launch_init<double>(const double*, uint64_t, alpb200_rg_state*, void*, void*, bool);
+template int launch_init<float>(const float*, uint64_t, alpb200_rg_state*, void*, void*, bool);
 
 // tail vector + NULLs: see fill_invalid_kernel in alp_prims.cuh
 template <typename PT>
@@ -269,7 +269,7 @@ int prim_rd_decode(PT* h_out, const typename Traits<PT>::UT* h_right, const uint
 }
 
 template <typename PT>
-int prim_init(const PT* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state) {
+int prim_init(const PT* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state, bool force_rd = false) {
 	if (!h_col || !h_state || offset >= n_values) { return fail(ALPB200_EINVAL, "prim_init: bad argument"); }
 	const uint64_t span = std::min<uint64_t>(ALPB200_ROWGROUP_SIZE, n_values - offset) / VEC * VEC;
 	if (span == 0) { return fail(ALPB200_EINVAL, "prim_init: the row-group holds no complete vector"); }
@@ -277,7 +277,7 @@ int prim_init(const PT* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_st
 	TRY(in.upload(h_col + offset, span * sizeof(PT)));
 	TRY(st.alloc(sizeof(alpb200_rg_state)));
 	TRY(ws.alloc(init_workspace_bytes(span)));
-	TRY(launch_init<PT>(in.as<PT>(), span, st.as<alpb200_rg_state>(), ws.p, nullptr));
+	TRY(launch_init<PT>(in.as<PT>(), span, st.as<alpb200_rg_state>(), ws.p, nullptr, force_rd));
 	TRY(finish_kernel());
 	TRY(st.download(h_state, sizeof(*h_state)));
 	return ALPB200_OK;
@@ -376,6 +376,12 @@ int alpb200_prim_init_f64(const double* col, uint64_t offset, uint64_t n_values,
 }
 int alpb200_prim_init_f32(const float* col, uint64_t offset, uint64_t n_values, alpb200_rg_state* st) {
 	return prim_init<float>(col, offset, n_values, st);
+}
+int alpb200_prim_rd_init_f64(const double* col, uint64_t offset, uint64_t n_values, alpb200_rg_state* st) {
+	return prim_init<double>(col, offset, n_values, st, true);
+}
+int alpb200_prim_rd_init_f32(const float* col, uint64_t offset, uint64_t n_values, alpb200_rg_state* st) {
+	return prim_init<float>(col, offset, n_values, st, true);
 }
 
 int alpb200_generate_f64(double* d_out, uint64_t n_values, uint64_t first_index, uint64_t seed, int kind, void* stream) {

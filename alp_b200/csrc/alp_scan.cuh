@@ -15,17 +15,29 @@
 namespace alpb200 {
 
 // decoded value at position p of an ALP vector, recomputed from the stage (run-time width)
-__device__ __forceinline__ double alp_value_at(const uint8_t* stage, const MetaRegs& m, uint32_t p, double) {
+__device__ __forceinline__ double alp_value_at(const uint8_t* stage, const MetaRegs& m, uint32_t p, double, bool /*decimal*/ = false) {
 	using T              = Traits<double>;
 	const uint32_t bw    = m.bw();
 	const uint64_t d     = bw ? extract64(reinterpret_cast<const uint64_t*>(stage), p & 15, (p >> 4) * bw, low_mask<uint64_t>(bw)) : 0;
 	return decode_value<double>((int64_t)(d + m.base()), T::fact10(m.f()), T::frac10(m.e()));
 }
-__device__ __forceinline__ double alp_value_at(const uint8_t* stage, const MetaRegs& m, uint32_t p, float) {
+__device__ __forceinline__ double alp_value_at(const uint8_t* stage, const MetaRegs& m, uint32_t p, float, bool decimal = false) {
 	using T           = Traits<float>;
 	const uint32_t bw = m.bw();
 	const uint32_t d  = bw ? extract32(reinterpret_cast<const uint32_t*>(stage), p & 31, (p >> 5) * bw, low_mask<uint32_t>(bw)) : 0;
+	if (decimal) {  // the slot's value as sum_alp_vector's decimal path counted it
+		return __dmul_rn(__dmul_rn((double)(int32_t)(d + m.a.x), __ll2double_rn(Traits<double>::fact10(m.f()))), Traits<double>::frac10(m.e()));
+	}
 	return (double)decode_value<float>((int32_t)(d + m.a.x), T::fact10(m.f()), T::frac10(m.e()));
+}
+// May a float vector take the decimal path?  Every slot's integer times 10^f must stay inside int32 (then the reference's
+// wrapping 32-bit product is the real product) and the FACT table entry must be the real power of ten (f <= 9).
+__device__ __forceinline__ bool sum_decimal_ok(const MetaRegs& m) {
+	const uint32_t bw = m.bw(), f = m.f();
+	if (bw > 31 || f > 9) { return false; }
+	const int64_t b   = (int64_t)(int32_t)m.a.x;
+	const int64_t mag = (b < 0 ? -b : b) + (1ll << bw);
+	return mag * Traits<double>::fact10(f) < (1ll << 31);
 }
 
 // Sum of the thread's 32 rows of an ALP vector, exception slots counted with their fill values.
@@ -38,7 +50,7 @@ __device__ __forceinline__ double alp_value_at(const uint8_t* stage, const MetaR
 // overflow: bw <= 57 and |base| < 2^56 (=> |X| < 2^62).  (10^f, f <= 18, is exact in double.)
 // The float path keeps the per-value decode: a float column's SUM is the sum of its FLOAT values, and fl32 rounding
 // of each value is visible at double precision.
-__device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, double) {
+__device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, double, bool /*decimal*/ = false) {
 	using T             = Traits<double>;
 	const int64_t  fact = T::fact10(m.f());
 	const double   frac = T::frac10(m.e());
@@ -81,11 +93,38 @@ __device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const Met
 	}
 	return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
-__device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, float) {
+// Floats, two semantics (alpb200_decode_sum_ex_f32):
+//   per value (default)   the sum, in double, of the FLOAT values the decoder produces — what decode + add gives, bit for bit up to
+//                         the order of the additions.  ~8 instructions per value (wrapping multiply, I2F, FMUL, F2F, DADD).
+//   ALPB200_SUM_DECIMAL   the sum of the DECIMALS the floats stand for: the thread adds its 32 integers exactly and converts once,
+//                         X * 10^f * 10^-e in double (the f64 recipe).  Differs from the per-value sum by the floats' own rounding:
+//                         |difference| <= 2^-23 * sum |x_i| (each float is within 2^-24 of its decimal, relatively, and the float
+//                         constant 10^-e within 2^-24 of the real one).  ~3 instructions per value.
+__device__ __forceinline__ double sum_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, float, bool decimal = false) {
 	using T             = Traits<float>;
 	const int32_t  fact = T::fact10(m.f());
 	const float    frac = T::frac10(m.e());
 	const uint32_t base = m.a.x;
+	if (decimal) {
+		uint64_t total = 0;
+		dispatch_width<0, 31>(m.bw(), [&](auto W) {
+			constexpr int BW = decltype(W)::value;
+			if constexpr (BW <= 27) {  // 32 fields of <= 27 bits: the sum fits 32 bits
+				uint32_t acc = 0;
+				unpack32_rows<BW>(stage, t, [&](int, uint32_t d) { acc += d; });
+				total = acc;
+			} else {
+				uint32_t acc_lo = 0, acc_hi = 0;
+				unpack32_rows<BW>(stage, t, [&](int, uint32_t d) {
+					acc_lo += d & 0xFFFFu;
+					acc_hi += d >> 16;
+				});
+				total = (uint64_t)acc_lo + ((uint64_t)acc_hi << 16);
+			}
+		});
+		const int64_t X = (int64_t)total + 32 * (int64_t)(int32_t)base;
+		return __dmul_rn(__dmul_rn(__ll2double_rn(X), __ll2double_rn(Traits<double>::fact10(m.f()))), Traits<double>::frac10(m.e()));
+	}
 	double         acc[4] = {0.0, 0.0, 0.0, 0.0};
 	dispatch_width<0, 32>(m.bw(), [&](auto W) {
 		constexpr int BW = decltype(W)::value;
@@ -140,14 +179,50 @@ __device__ __forceinline__ double sum_vector_slow(const ColView& col, const Meta
 	return acc;
 }
 
+// The first 32 K exceptions of a vector (K per lane: lane t holds ranks t, t + 32, ...), fetched one vector ahead so that the
+// exception loop never waits for memory; positions are packed two to a register.
+template <typename UT, int K>
+struct ExcRegsK {
+	UT       val[K];
+	uint32_t pos2[(K + 1) / 2];
+	__device__ __forceinline__ uint32_t pos(int k) const { return (pos2[k >> 1] >> (16 * (k & 1))) & 0xFFFFu; }
+};
+template <typename UT, int K>
+__device__ __forceinline__ ExcRegsK<UT, K> load_exceptions_k(const ColView& col, const MetaRegs& m, int t) {
+	ExcRegsK<UT, K> x;
+#pragma unroll
+	for (int k = 0; k < (K + 1) / 2; k++) {
+		x.pos2[k] = 0;
+	}
+	const uint32_t  cnt = m.exc_cnt();
+	const UT*       ev  = static_cast<const UT*>(col.exc_val) + m.exc_off();
+	const uint16_t* ep  = col.exc_pos + m.exc_off();
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		const uint32_t i = (uint32_t)t + 32u * k;
+		x.val[k]         = 0;
+		if (i < cnt) {
+			x.val[k] = __ldg(ev + i);
+			x.pos2[k >> 1] |= (uint32_t)__ldg(ep + i) << (16 * (k & 1));
+		}
+	}
+	return x;
+}
+template <typename PT>
+struct SumCfg {
+	static constexpr int EXC_K = sizeof(PT) == 4 ? 4 : 1;  // floats: exception-heavy columns are the norm (6 bytes per exception)
+};
+
 // register allocation limited for 32 resident warps per SM (64 registers, no spills): against 24 x 80 registers the f64
 // scan gains 4-8 % (0.293 -> 0.280 ms per 2^29 values on config 2)
 template <typename PT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
                                                                   double* __restrict__ sum, uint32_t stage_bytes,
                                                                   unsigned long long* __restrict__ counter,
-                                                                  const unsigned long long* __restrict__ oversize) {
+                                                                  const unsigned long long* __restrict__ oversize, uint32_t flags) {
 	using UT = typename Traits<PT>::UT;
+	constexpr int K = SumCfg<PT>::EXC_K;
+	using XR        = ExcRegsK<UT, K>;
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
 	if (oversize != nullptr && *oversize != 0) {  // the hint was too small for this call (hint_check_kernel): slow, correct
@@ -204,15 +279,15 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 	MetaRegs nxt      = cur;
 	if (has_next) { nxt = load_meta(meta + v_next); }
 	issue(cur, 0);
-	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
-	uint32_t    phase = 0;
-	double      acc   = 0.0;
+	XR       xcur  = load_exceptions_k<UT, K>(col, cur, t);
+	uint32_t phase = 0;
+	double   acc   = 0.0;
 	for (int s = 0;; s ^= 1) {
-		ExcRegs<UT> xnxt = xcur;
+		XR xnxt = xcur;
 		if (has_next) {
 			issue(nxt, s ^ 1);
-			xnxt = load_exceptions<UT>(col, nxt, t);
-			prefetch_exception_tail(col, nxt, t, sizeof(UT));
+			xnxt = load_exceptions_k<UT, K>(col, nxt, t);
+			if (nxt.exc_cnt() > 32u * K) { prefetch_exception_tail(col, nxt, t, sizeof(UT)); }
 		}
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
@@ -227,18 +302,29 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 		const UT*       ev  = static_cast<const UT*>(col.exc_val) + cur.exc_off();
 		const uint16_t* ep  = col.exc_pos + cur.exc_off();
 		if (cur.scheme() == ALPB200_SCHEME_ALP) {
-			acc += sum_alp_vector(stg, cur, t, PT());
-			for (uint32_t i = t; i < cnt; i += 32) {  // exception: + true value - decoded fill value
-				const uint32_t p   = i < 32 ? xcur.pos : ep[i];
-				const UT       val = i < 32 ? xcur.val : ev[i];
-				acc += (double)Traits<PT>::from_bits(val) - alp_value_at(stg, cur, p, PT());
+			bool decimal = false;
+			if constexpr (sizeof(PT) == 4) { decimal = (flags & ALPB200_SUM_DECIMAL) != 0 && sum_decimal_ok(cur); }
+			acc += sum_alp_vector(stg, cur, t, PT(), decimal);
+			// exception: + true value - what the slot was counted as
+#pragma unroll
+			for (int k = 0; k < K; k++) {
+				if ((uint32_t)t + 32u * k < cnt) { acc += (double)Traits<PT>::from_bits(xcur.val[k]) - alp_value_at(stg, cur, xcur.pos(k), PT(), decimal); }
+			}
+			for (uint32_t i = (uint32_t)t + 32u * K; i < cnt; i += 32) {
+				acc += (double)Traits<PT>::from_bits(ev[i]) - alp_value_at(stg, cur, ep[i], PT(), decimal);
 			}
 		} else {
 			acc += sum_rd_vector<PT>(stg, cur, t);
-			for (uint32_t i = t; i < cnt; i += 32) {
-				const uint32_t p    = i < 32 ? xcur.pos : ep[i];
-				const uint32_t left = (uint32_t)((i < 32 ? xcur.val : ev[i]) & 0xFFFFu);
-				acc += rd_value<PT>(stg, cur, p, true, left) - rd_value<PT>(stg, cur, p, false, 0);
+#pragma unroll
+			for (int k = 0; k < K; k++) {
+				if ((uint32_t)t + 32u * k < cnt) {
+					const uint32_t p = xcur.pos(k);
+					acc += rd_value<PT>(stg, cur, p, true, (uint32_t)(xcur.val[k] & 0xFFFFu)) - rd_value<PT>(stg, cur, p, false, 0);
+				}
+			}
+			for (uint32_t i = (uint32_t)t + 32u * K; i < cnt; i += 32) {
+				const uint32_t p = ep[i];
+				acc += rd_value<PT>(stg, cur, p, true, (uint32_t)(ev[i] & 0xFFFFu)) - rd_value<PT>(stg, cur, p, false, 0);
 			}
 		}
 		__syncwarp();

@@ -412,6 +412,20 @@ def config_block(kind, n, dev, rank, peak, steps, with_cpu, cpu_seconds):
     alp_b200.decode_sum(col, out=acc)
     want = float(x.sum(dtype=torch.float64).item())
     got = float(acc.item())
+    dec_block = None
+    if vb == 4:  # float columns: the decimal-sum variant (integers added exactly, one conversion per thread; include/alp_b200.h)
+        for _ in range(3):
+            alp_b200.decode_sum(col, out=acc, flags=alp_b200.SUM_DECIMAL)
+        dscan_ms = cuda_ms(lambda: alp_b200.decode_sum(col, out=acc, flags=alp_b200.SUM_DECIMAL), steps)
+        acc.zero_()
+        alp_b200.decode_sum(col, out=acc, flags=alp_b200.SUM_DECIMAL)
+        dgot = float(acc.item())
+        sum_abs = float(x.abs().sum(dtype=torch.float64).item())
+        dec_block = {"ms": dscan_ms, "read_GBps": read_bytes / (dscan_ms * 1e-3) / 1e9, "roofline_frac": read_bytes / (dscan_ms * 1e-3) / 1e9 / peak,
+                     "GBps_decoded_equivalent": n * vb / (dscan_ms * 1e-3) / 1e9,
+                     "abs_diff_over_sum_abs": abs(dgot - want) / max(sum_abs, 1e-300), "bound": 2.0 ** -23,
+                     "semantics": "ALPB200_SUM_DECIMAL: sum of the decimals the floats stand for (|diff| <= 2^-23 * sum|x|)"}
+        assert dec_block["abs_diff_over_sum_abs"] <= 2.0 ** -23, "decimal SUM outside its stated bound"
 
     def rate(ms, nbytes):
         return nbytes / (ms * 1e-3) / 1e9
@@ -435,6 +449,8 @@ def config_block(kind, n, dev, rank, peak, steps, with_cpu, cpu_seconds):
         "scan_sum": {"ms": scan_ms, "GBps_decoded_equivalent": rate(scan_ms, n * vb), "read_GBps": rate(scan_ms, read_bytes),
                      "roofline_frac": rate(scan_ms, read_bytes) / peak, "rel_err_vs_torch_sum": abs(got - want) / max(abs(want), 1e-300)},
     }
+    if dec_block is not None:
+        block["scan_sum_decimal"] = dec_block
     if with_cpu:
         ns = min(n, CPU_SAMPLE_VALUES)
         block["cpu"] = cpu_legs(kind, ns, host_threads(), cpu_seconds, x_host=None if ref_bench_binary() else x[:ns].cpu().numpy())

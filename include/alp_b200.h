@@ -28,6 +28,7 @@ extern "C" {
 #define ALPB200_VECTOR_SIZE 1024u          /* config.hpp:11 VECTOR_SIZE */
 #define ALPB200_ROWGROUP_VECTORS 100u      /* config.hpp:13 N_VECTORS_PER_ROWGROUP */
 #define ALPB200_ROWGROUP_SIZE 102400u      /* config.hpp:15 ROWGROUP_SIZE */
+#define ALPB200_ROWGROUP_SAMPLES_JUMP 12u  /* config.hpp:17-19: (ROWGROUP_SIZE / 8) / VECTOR_SIZE: every 12th vector is sampled */
 #define ALPB200_MAX_K 5                    /* config.hpp:22 MAX_K_COMBINATIONS */
 #define ALPB200_RD_DICT_SIZE 8             /* config.hpp:25 MAX_RD_DICTIONARY_SIZE */
 #define ALPB200_MAX_SAMPLES 288            /* 9 sampled vectors x 32 values (sampler.hpp:14-52) */
@@ -235,6 +236,16 @@ int alpb200_decode_sum_f64(const alpb200_column* col, uint64_t first_vector, uin
                            void* stream);
 int alpb200_decode_sum_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum,
                            void* stream);
+/* The same with flags.  ALPB200_SUM_DECIMAL (floats; doubles always work this way, where it is at least as accurate as adding
+ * the decoded doubles): a vector's non-exception slots are added as INTEGERS and converted once, X * 10^f * 10^-e in double —
+ * the sum of the decimals the floats stand for instead of the sum of the floats.  The two differ by the floats' own rounding:
+ * |difference| <= 2^-23 * sum |x_i|.  About 2x faster on float columns (3 instead of 8 instructions per value).  Vectors whose
+ * integers times 10^f could leave int32 (where the reference's 32-bit product wraps) keep the per-value path. */
+#define ALPB200_SUM_DECIMAL 1u
+int alpb200_decode_sum_ex_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum, uint32_t flags,
+                              void* stream);
+int alpb200_decode_sum_ex_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum, uint32_t flags,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host engine calls; copies are part of the call).
@@ -334,6 +345,10 @@ int alpb200_prim_rd_decode_f32(float* h_out, const uint32_t* h_right, const uint
  * the values [offset, min(offset+102400, n_values)) form the row-group. */
 int alpb200_prim_init_f64(const double* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
 int alpb200_prim_init_f32(const float* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
+/* alp::rd_encoder<PT>::init (rd.hpp:180-185) on its own: the row-group is made an ALP_RD row-group whatever the ALP search
+ * would have said — cut position, dictionary and exception indices from the same first-level sample. */
+int alpb200_prim_rd_init_f64(const double* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
+int alpb200_prim_rd_init_f32(const float* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
 
 /* ------------------------------------------------------------------------------------------------
  * Synthetic column generators on the device (stateless splitmix64 per index so that

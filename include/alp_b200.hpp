@@ -179,6 +179,25 @@ inline void from_pod(const alpb200_rg_state& s, state<PT>& stt) {
 // dispatch on the value type
 inline int init(const double* c, uint64_t o, uint64_t n, alpb200_rg_state* s) { return alpb200_prim_init_f64(c, o, n, s); }
 inline int init(const float* c, uint64_t o, uint64_t n, alpb200_rg_state* s) { return alpb200_prim_init_f32(c, o, n, s); }
+inline int rd_init(const double* c, uint64_t o, uint64_t n, alpb200_rg_state* s) { return alpb200_prim_rd_init_f64(c, o, n, s); }
+inline int rd_init(const float* c, uint64_t o, uint64_t n, alpb200_rg_state* s) { return alpb200_prim_rd_init_f32(c, o, n, s); }
+//! The first-level sample as the caller's `sample_arr` would hold it (sampler.hpp:14-52 restricted to whole vectors, which is what
+//! the device init samples): values 0, 32, ..., 992 of vectors 0, 12, 24, ... of the row-group.  Returns the number of samples.
+//! (An output parameter filled from the caller's own host column; the search itself runs on the device.)
+template <typename PT>
+inline size_t fill_sample(const PT* column, size_t offset, size_t n_values, PT* sample_arr) {
+	const size_t in_rowgroup = n_values - offset < size_t(ALPB200_ROWGROUP_SIZE) ? n_values - offset : size_t(ALPB200_ROWGROUP_SIZE);
+	const size_t vectors     = in_rowgroup / ALPB200_VECTOR_SIZE;
+	size_t       n           = 0;
+	for (size_t v = 0; v < vectors; v += ALPB200_ROWGROUP_SAMPLES_JUMP) {
+		const PT* vec = column + offset + v * ALPB200_VECTOR_SIZE;
+		for (size_t i = 0; i < size_t(ALPB200_VECTOR_SIZE); i += 32) {
+			if (sample_arr) { sample_arr[n] = vec[i]; }
+			n++;
+		}
+	}
+	return n;
+}
 inline int encode(const double* in, const alpb200_rg_state* s, double* exc, uint16_t* pos, uint16_t* cnt, int64_t* enc, uint8_t* e, uint8_t* f) {
 	return alpb200_prim_encode_f64(in, s, exc, pos, cnt, enc, e, f);
 }
@@ -212,11 +231,12 @@ struct encoder {
 	using ST = typename inner_t<PT>::st;
 
 	//! once per row-group: first-level sampling + top-k (exponent, factor) search + scheme decision.
-	//! `sample_arr` is accepted for signature compatibility; the samples never leave the device.
-	static inline void init(const PT* data_column, const size_t column_offset, const size_t tuples_count, PT* /*sample_arr*/, state<PT>& stt) {
+	//! `sample_arr` receives the first-level sample like in the reference (encoder.hpp:420-427); the search reads the column on the device.
+	static inline void init(const PT* data_column, const size_t column_offset, const size_t tuples_count, PT* sample_arr, state<PT>& stt) {
 		alpb200_rg_state s;
 		check_(detail::init(data_column, column_offset, tuples_count, &s));
 		detail::from_pod(s, stt);
+		stt.sampled_values_n = detail::fill_sample(data_column, column_offset, tuples_count, sample_arr);
 		if (stt.scheme == Scheme::ALP_RD) {
 			// the reference decides the scheme here and builds the dictionary in rd_encoder<PT>::init; the device init does
 			// both at once, so only the scheme is reported until rd_encoder<PT>::init is called
@@ -257,11 +277,12 @@ template <typename PT>
 struct rd_encoder {
 	using UT = typename inner_t<PT>::ut;
 
-	static inline void init(const PT* data_column, size_t column_offset, size_t tuples_count, PT* /*sample_arr*/, state<PT>& stt) {
+	//! rd.hpp:180-185: builds cut + dictionary for ANY row-group (callers that force ALP_RD, e.g. bench_alp_cutter_encode.cpp:110)
+	static inline void init(const PT* data_column, size_t column_offset, size_t tuples_count, PT* sample_arr, state<PT>& stt) {
 		alpb200_rg_state s;
-		check_(detail::init(data_column, column_offset, tuples_count, &s));
-		if (s.scheme != ALPB200_SCHEME_ALP_RD) { throw gpu_error(ALPB200_EINVAL, "rd_encoder::init: the row-group is not an ALP_RD row-group"); }
+		check_(detail::rd_init(data_column, column_offset, tuples_count, &s));
 		detail::from_pod(s, stt);
+		stt.sampled_values_n = detail::fill_sample(data_column, column_offset, tuples_count, sample_arr);
 	}
 	static inline void encode(const PT* dbl_arr, uint16_t* exceptions, uint16_t* exception_positions, uint16_t* exceptions_count_p,
 	                          UT* right_parts, uint16_t* left_parts, state<PT>& stt) {

@@ -32,6 +32,23 @@ static int run_case(const PT* input_arr, uint32_t golden_bw, uint32_t golden_exc
 
 	alp::encoder<PT>::init(input_arr, 0, N, sample_arr.data(), stt);
 	if (static_cast<uint32_t>(stt.scheme) != want_scheme) { return 1; }
+	// the caller's sample array is filled like the reference's (encoder.hpp:420-427, sampler.hpp:14-52): values 0, 32, ..., 992
+	bad += stt.sampled_values_n != 32;
+	for (size_t i = 0; i < 32; i++) {
+		bad += !same_value(sample_arr[i], input_arr[32 * i]);
+	}
+	{
+		// rd.hpp:180-185: rd_encoder<PT>::init builds a dictionary for ANY row-group (bench_alp_cutter_encode.cpp:110 calls it on
+		// columns the ALP search would keep): forced ALP_RD must round-trip every vector, decimal or not
+		alp::state<PT> forced;
+		alp::rd_encoder<PT>::init(input_arr, 0, N, sample_arr.data(), forced);
+		bad += forced.scheme != alp::Scheme::ALP_RD;
+		alp::rd_encoder<PT>::encode(input_arr, rd_exc_arr.data(), pos_arr.data(), exc_c_arr.data(), right_arr.data(), left_arr.data(), forced);
+		alp::rd_encoder<PT>::decode(glue_arr.data(), right_arr.data(), left_arr.data(), rd_exc_arr.data(), pos_arr.data(), exc_c_arr.data(), forced);
+		for (size_t i = 0; i < N; i++) {
+			bad += !same_value(input_arr[i], glue_arr[i]);
+		}
+	}
 	switch (stt.scheme) {
 	case alp::Scheme::ALP_RD: {
 		alp::rd_encoder<PT>::init(input_arr, 0, N, sample_arr.data(), stt);
@@ -65,6 +82,30 @@ static int run_case(const PT* input_arr, uint32_t golden_bw, uint32_t golden_exc
 	return bad;
 }
 
+// the 8-bit-lane overloads (fastlanes/ffor.hpp:10,15; unffor.hpp:10,15): every width, round trip
+static int run_u8() {
+	std::vector<uint8_t> in(1024), packed(1024), out(1024);
+	std::vector<int8_t>  sin(1024), spacked(1024), sout(1024);
+	int                  bad = 0;
+	for (uint8_t bw = 0; bw <= 8; bw++) {
+		const uint8_t base = static_cast<uint8_t>(17 * bw + 3);
+		for (size_t i = 0; i < 1024; i++) {
+			in[i]  = static_cast<uint8_t>(base + ((i * 7 + i / 128) & ((1u << bw) - 1u)));
+			sin[i] = static_cast<int8_t>(in[i]);
+		}
+		ffor::ffor(in.data(), packed.data(), bw, &base);
+		unffor::unffor(packed.data(), out.data(), bw, &base);
+		const int8_t sbase = static_cast<int8_t>(base);
+		ffor::ffor(sin.data(), spacked.data(), bw, &sbase);
+		unffor::unffor(spacked.data(), sout.data(), bw, &sbase);
+		for (size_t i = 0; i < 1024; i++) {
+			bad += out[i] != in[i];
+			bad += sout[i] != sin[i];
+		}
+	}
+	return bad;
+}
+
 int main(int argc, char** argv) {
 	if (argc < 2) { return 2; }
 	FILE* f = std::fopen(argv[1], "rb");
@@ -85,6 +126,14 @@ int main(int argc, char** argv) {
 		return 3;
 	}
 	std::fclose(f);
+	try {
+		const int b8 = run_u8();
+		if (b8) { std::printf("8-bit lanes: %d mismatches\n", b8); }
+		bad += b8 != 0;
+	} catch (const alp::gpu_error& e) {
+		std::printf("gpu_error %d: %s\n", e.code, e.what());
+		return 3;
+	}
 	std::printf("cases %d bad %d\n", n, bad);
 	return bad ? 1 : 0;
 }

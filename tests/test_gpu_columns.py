@@ -615,6 +615,45 @@ def test_fused_decode_sum(kind):
     assert abs(part - want_part) <= 1e-9 * max(1.0, abs(want_part))
 
 
+def test_decimal_sum_of_a_float_column(checker):
+    """ALPB200_SUM_DECIMAL (include/alp_b200.h): integers added exactly, one conversion per thread.  Checked against sums made
+    on the CHECKER's side: the default path against the float-by-float float64 sum of the checker's decoded column (1e-12
+    relative), the decimal path within its stated bound 2^-23 * sum|x| of it — also for a column whose vectors must NOT take
+    the decimal path (integers times 10^f beyond int32)."""
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    rng = np.random.default_rng(11)
+    cols = {
+        "config4": pyoracle.generate(3 * 102400 + 7 * 1024, 4),
+        "two_decimals": (rng.integers(-500000, 500000, size=1024 * 150) / 100.0).astype(np.float32),
+        "wide_integers": rng.integers(-(1 << 30), 1 << 30, size=1024 * 120).astype(np.float32),
+        "near_int32": (rng.integers(0, 2000000, size=1024 * 110) / 1000.0).astype(np.float32),
+    }
+    for name, x in cols.items():
+        col = alp_b200.encode(torch.from_numpy(x).to(_dev()))
+        col.read_totals()
+        decoded = checker.decode_column(col.to_host())
+        assert decoded.tobytes() == x.tobytes(), name
+        want = float(np.sum(decoded.astype(np.float64)))
+        sum_abs = float(np.sum(np.abs(decoded.astype(np.float64))))
+        got = float(alp_b200.decode_sum(col).item())
+        assert abs(got - want) <= 1e-12 * sum_abs, (name, got, want)
+        dec = float(alp_b200.decode_sum(col, flags=alp_b200.SUM_DECIMAL).item())
+        assert abs(dec - want) <= 2.0**-23 * sum_abs, (name, dec, want, sum_abs)
+        part = float(alp_b200.decode_sum(col, first=3, n=41, flags=alp_b200.SUM_DECIMAL).item())
+        want_part = float(np.sum(decoded[3 * 1024 : 44 * 1024].astype(np.float64)))
+        assert abs(part - want_part) <= 2.0**-23 * float(np.sum(np.abs(decoded[3 * 1024 : 44 * 1024].astype(np.float64)))), name
+    # doubles accept the flag and ignore it
+    xd = alp_b200.generate(102400, 2, _dev())
+    cd = alp_b200.encode(xd)
+    cd.read_totals()
+    a, b = float(alp_b200.decode_sum(cd).item()), float(alp_b200.decode_sum(cd, flags=alp_b200.SUM_DECIMAL).item())
+    assert abs(a - b) <= 1e-12 * abs(a)
+
+
 def test_fused_decode_sum_propagates_nan():
     import torch
 
