@@ -131,6 +131,8 @@ struct TileIO {
 	__device__ __forceinline__ void store(std::integral_constant<int, R>, UT v) {
 		tile[Map<PT>::index(t, R)] = v;
 	}
+	__device__ __forceinline__ UT   load_row(int r) { return tile[Map<PT>::index(t, r)]; }
+	__device__ __forceinline__ void store_row(int r, UT v) { tile[Map<PT>::index(t, r)] = v; }
 	// value i of the vector (second-level sampling; before the analysis overwrites the tile): no trip to global memory
 	__device__ __forceinline__ PT sample(const PT*, int i) const { return Traits<PT>::from_bits(tile[i]); }
 	// start over: the tile was overwritten with encoded integers; every thread restores ITS OWN slots from global memory
@@ -178,6 +180,9 @@ struct TileIO {
 //         (float, f = 10: FACT[10] is the reference's out-of-bounds 0, so P = 0 and nothing wraps; 10^f is taken as 0.)
 // (FastLimits<PT>: alp_device.cuh)
 
+#ifndef ALPB200_ANALYZE_UNROLL
+#define ALPB200_ANALYZE_UNROLL 8  // rows per iteration of the analysis loop (32 = fully unrolled)
+#endif
 // what the 32 rows of a thread accumulate
 template <typename PT>
 struct RowAcc {
@@ -198,43 +203,51 @@ __device__ __forceinline__ bool analyze_rows(IO& io, int e, int f, RowAcc<PT>& a
 	const ST       fa  = T::fact10(f);
 	const PT       fap = FL::fact_fp(f);
 	bool           suspicious = false;
-	static_for<0, 32>([&](auto R) {
-		constexpr int r  = decltype(R)::value;
-		const UT      xb = io.load(R);
-		ST            enc;
-		bool          exc;
-		if constexpr (FAST) {
-			const PT       tr  = T::magic_round(T::mul(T::mul(T::from_bits(xb), ex), frf));  // encoder.hpp:83,87
-			const PT       pd  = T::mul(tr, fap);
-			const uint32_t key = FL::key(pd);
-			enc                = FL::cast_sat(tr);
-			suspicious |= key == FL::BIG;
-			const PT dec = T::mul(pd, fre);
-			exc          = (T::bits(dec) != xb) | (key > FL::BIG);
-		} else {
-			enc          = encode_value<PT, false>(T::from_bits(xb), ex, frf);  // encoder.hpp:345
-			const PT dec = decode_value<PT>(enc, fa, fre);                       // :347
-			exc          = T::bits(dec) != xb;
-		}
-		if constexpr (IO::KEEP_EXC) {
-			if (!exc) { io.store(R, (UT)enc); }  // (a predicated store: no extra instruction)
-		} else {
-			io.store(R, (UT)enc);
-		}
-		if (exc) { acc.myexc |= 1u << r; }
-		if (!exc) {  // exceptions take no part in min / max (predicated, no branch)
-			if constexpr (sizeof(PT) == 8) {
-				const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
-				acc.lo_min = min(acc.lo_min, lo);
-				acc.lo_max = max(acc.lo_max, lo);
-				acc.hi_and &= hi;
-				acc.hi_or |= hi;
+	// ANALYZE_UNROLL rows per loop iteration (not all 32 unrolled): the kernel's instruction footprint is what the warps of an
+	// SM share in the instruction caches, and this loop is the largest piece of it
+#pragma unroll 1
+	for (int r0 = 0; r0 < 32; r0 += ALPB200_ANALYZE_UNROLL) {
+		uint32_t excbits = 0;
+		static_for<0, ALPB200_ANALYZE_UNROLL>([&](auto R) {
+			constexpr int i  = decltype(R)::value;
+			const int     r  = r0 + i;
+			const UT      xb = io.load_row(r);
+			ST            enc;
+			bool          exc;
+			if constexpr (FAST) {
+				const PT       tr  = T::magic_round(T::mul(T::mul(T::from_bits(xb), ex), frf));  // encoder.hpp:83,87
+				const PT       pd  = T::mul(tr, fap);
+				const uint32_t key = FL::key(pd);
+				enc                = FL::cast_sat(tr);
+				suspicious |= key == FL::BIG;
+				const PT dec = T::mul(pd, fre);
+				exc          = (T::bits(dec) != xb) | (key > FL::BIG);
 			} else {
-				acc.mn = min(acc.mn, enc);
-				acc.mx = max(acc.mx, enc);
+				enc          = encode_value<PT, false>(T::from_bits(xb), ex, frf);  // encoder.hpp:345
+				const PT dec = decode_value<PT>(enc, fa, fre);                       // :347
+				exc          = T::bits(dec) != xb;
 			}
-		}
-	});
+			if constexpr (IO::KEEP_EXC) {
+				if (!exc) { io.store_row(r, (UT)enc); }  // (a predicated store: no extra instruction)
+			} else {
+				io.store_row(r, (UT)enc);
+			}
+			if (exc) { excbits |= 1u << i; }
+			if (!exc) {  // exceptions take no part in min / max (predicated, no branch)
+				if constexpr (sizeof(PT) == 8) {
+					const uint32_t lo = (uint32_t)(uint64_t)enc, hi = (uint32_t)((uint64_t)enc >> 32);
+					acc.lo_min = min(acc.lo_min, lo);
+					acc.lo_max = max(acc.lo_max, lo);
+					acc.hi_and &= hi;
+					acc.hi_or |= hi;
+				} else {
+					acc.mn = min(acc.mn, enc);
+					acc.mx = max(acc.mx, enc);
+				}
+			}
+		});
+		acc.myexc |= excbits << r0;
+	}
 	if constexpr (FAST) { return !__any_sync(FULL, suspicious); }
 	return true;
 }
@@ -536,8 +549,13 @@ __device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&&
 #define ALPB200_ENC_LOOKBACK 1  // 1: blocks resolve their prefix by look-back from the scanner's anchors; 0: per-block prefixes from the scanner
 #endif
 #ifndef ALPB200_ENC_SPIN_NS
-#define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth)
+#define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth); 0 = none
 #endif
+__device__ __forceinline__ void enc_backoff() {
+#if ALPB200_ENC_SPIN_NS > 0
+	__nanosleep(ALPB200_ENC_SPIN_NS);
+#endif
+}
 
 // ---- placement: in-order prefix sums over thread blocks ---------------------------------------------------------------
 // Every block publishes its aggregate (packed 128-byte units << AGG_SHIFT | exception slots) and then waits for its exclusive
@@ -663,7 +681,7 @@ __device__ __forceinline__ void scan_anchors(const uint64_t* aggregates, uint64_
 			}
 		}
 		G += done;
-		if (done == 0) { __nanosleep(40); }
+		if (done == 0) { enc_backoff(); }
 	}
 }
 
@@ -683,7 +701,7 @@ __device__ __forceinline__ uint64_t lookback_prefix(const uint64_t* aggregates, 
 			G           = g - (uint32_t)j;
 			break;
 		}
-		__nanosleep(ALPB200_ENC_SPIN_NS);  // the scanner is more than LB_DEPTH groups behind: wait for it
+		enc_backoff();  // the scanner is more than LB_DEPTH groups behind: wait for it
 	}
 	// aggregates of blocks [32 G, bid): chunk k = blocks 32 (G + k) .. 32 (G + k) + 31, one per lane; all loads go out at once
 	uint64_t v[LB_DEPTH];
@@ -698,7 +716,7 @@ __device__ __forceinline__ uint64_t lookback_prefix(const uint64_t* aggregates, 
 		pending = pending || !(v[k] & SCAN_VALID);
 	}
 	while (__any_sync(FULL, pending)) {  // the newest predecessors are still analysing: re-poll only what is missing
-		__nanosleep(ALPB200_ENC_SPIN_NS);
+		enc_backoff();
 		pending = false;
 #pragma unroll
 		for (uint32_t k = 0; k < LB_DEPTH; k++) {
@@ -964,7 +982,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 			excl = lookback_prefix(aggregates, prefixes, bid, t);  // (`prefixes` holds the anchors in this scheme)
 #else
 			if (t == 0) {
-				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { __nanosleep(ALPB200_ENC_SPIN_NS); }
+				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { enc_backoff(); }
 				excl &= SCAN_VAL;
 			}
 #endif
