@@ -180,20 +180,16 @@ __device__ __forceinline__ double sum_vector_slow(const ColView& col, const Meta
 }
 
 // The first 32 K exceptions of a vector (K per lane: lane t holds ranks t, t + 32, ...), fetched one vector ahead so that the
-// exception loop never waits for memory; positions are packed two to a register.
+// exception loop never waits for memory.
 template <typename UT, int K>
 struct ExcRegsK {
 	UT       val[K];
-	uint32_t pos2[(K + 1) / 2];
-	__device__ __forceinline__ uint32_t pos(int k) const { return (pos2[k >> 1] >> (16 * (k & 1))) & 0xFFFFu; }
+	uint16_t raw_pos[K];  // (nothing is computed on the loaded words here: a use would make the warp wait for the load right away)
+	__device__ __forceinline__ uint32_t pos(int k) const { return raw_pos[k]; }
 };
 template <typename UT, int K>
 __device__ __forceinline__ ExcRegsK<UT, K> load_exceptions_k(const ColView& col, const MetaRegs& m, int t) {
 	ExcRegsK<UT, K> x;
-#pragma unroll
-	for (int k = 0; k < (K + 1) / 2; k++) {
-		x.pos2[k] = 0;
-	}
 	const uint32_t  cnt = m.exc_cnt();
 	const UT*       ev  = static_cast<const UT*>(col.exc_val) + m.exc_off();
 	const uint16_t* ep  = col.exc_pos + m.exc_off();
@@ -201,9 +197,10 @@ __device__ __forceinline__ ExcRegsK<UT, K> load_exceptions_k(const ColView& col,
 	for (int k = 0; k < K; k++) {
 		const uint32_t i = (uint32_t)t + 32u * k;
 		x.val[k]         = 0;
+		x.raw_pos[k]     = 0;
 		if (i < cnt) {
-			x.val[k] = __ldg(ev + i);
-			x.pos2[k >> 1] |= (uint32_t)__ldg(ep + i) << (16 * (k & 1));
+			x.val[k]     = __ldg(ev + i);
+			x.raw_pos[k] = __ldg(ep + i);
 		}
 	}
 	return x;

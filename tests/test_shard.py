@@ -110,3 +110,50 @@ def test_slice_column_of_a_completion_order_layout(port):
         s = shard.slice_column(t, first, count)
         h = shard.tensors_to_host_column(s, 8)
         assert port.decode_column(h).tobytes() == x[first * 1024 : (first + count) * 1024].tobytes()
+
+
+def _nccl_worker(rank, world, port, kind, n_values, out_dir):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import alp_b200
+    from alp_b200 import shard
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    vb = 4 if kind == 4 else 8
+    tensors = None
+    if rank == 0:  # the column is encoded on GPU 0 and handed out from there
+        col = alp_b200.encode(alp_b200.generate(n_values, kind, dev))
+        tensors = shard.column_tensors(col)
+    mine, (first, count) = shard.scatter_column(tensors, src=0, value_bytes=vb, device=dev)
+    ok = mine["meta"].shape[0] == count
+    if count:
+        got = alp_b200.decode(shard.tensors_to_device_column(mine, vb, dev))
+        want = alp_b200.generate(count * 1024, kind, dev, first_index=first * 1024)  # stateless generator: any rank can re-create its slice
+        ibits = torch.int64 if vb == 8 else torch.int32
+        ok = ok and bool(torch.equal(got.view(ibits), want.view(ibits)))
+    flags = torch.tensor([1 if ok else 0, count], dtype=torch.int64, device=dev)
+    gathered = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, flags)
+    if rank == 0:
+        good = all(int(g[0]) == 1 for g in gathered) and sum(int(g[1]) for g in gathered) == n_values // 1024
+        with open(os.path.join(out_dir, "nccl_%d_%d" % (kind, world)), "w") as fh:
+            fh.write("ok" if good else "bad %s" % [g.tolist() for g in gathered])
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [2, 3, 4])
+def test_nccl_scatter_shards_decode_on_their_gpus(kind, tmp_path):
+    """BASELINE config 5 ("scattered across the GPUs"): a column encoded on GPU 0 goes out as whole-row-group shards over NCCL
+    point-to-point sends and every GPU decodes its shard bit-exactly.  Needs two devices (skipped otherwise)."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two CUDA devices")
+    n_values = 1024 * 937  # 9 full row-groups + a short one
+    mp.spawn(_nccl_worker, args=(world, _free_port(), kind, n_values, str(tmp_path)), nprocs=world, join=True)
+    assert open(os.path.join(str(tmp_path), "nccl_%d_%d" % (kind, world))).read() == "ok"

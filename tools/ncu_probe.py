@@ -36,7 +36,8 @@ def main():
     alp_b200.encode(x, st, col=col, workspace=ws, ordered=ordered)
     col.read_totals()  # also learns the widest block: the decoders size their stages from it
     for _ in range(3):
-        alp_b200.encode(x, st, col=col, workspace=ws, ordered=ordered)
+        if what.startswith("encode"):
+            alp_b200.encode(x, st, col=col, workspace=ws, ordered=ordered)
         if what == "decode":
             alp_b200.decode(col, out=out)
         if what == "sum":
