@@ -23,6 +23,9 @@
 #ifndef ALPB200_DEC_MINBLOCKS
 #define ALPB200_DEC_MINBLOCKS 2  // resident CTAs per SM the register allocation is limited for
 #endif
+#ifndef ALPB200_DEC_MINBLOCKS_F32
+#define ALPB200_DEC_MINBLOCKS_F32 2  // (three CTAs of 80 registers were tried for floats: spills, 0.304 vs 0.285 ms per 2^28 values of config 4)
+#endif
 #ifndef ALPB200_DEC_STREAMING_STORES
 #define ALPB200_DEC_STREAMING_STORES 0  // 1: st.global.cs for the decoded values (written once, never re-read)
 #endif
@@ -192,6 +195,39 @@ __device__ __forceinline__ ExcRegs<UT> load_exceptions(const ColView& col, const
 	}
 	return x;
 }
+// Exceptions 32 .. 32 (1 + TAIL) - 1 of an ALP vector (lane t: ranks t + 32, t + 64, ...), also fetched one vector ahead.  Float
+// columns are where exception-heavy vectors are the norm (6 bytes per exception: BASELINE config 4 has 90 per vector); with the
+// tail in registers their patch is stores only.  Nothing is computed on the loaded words here (a use would make the warp wait).
+template <typename PT>
+struct DecCfg {
+	static constexpr int EXC_TAIL  = sizeof(PT) == 4 ? 3 : 0;  // floats: 128 exceptions per vector in registers
+	static constexpr int MINBLOCKS = sizeof(PT) == 4 ? ALPB200_DEC_MINBLOCKS_F32 : ALPB200_DEC_MINBLOCKS;
+};
+template <typename UT, int N>
+struct ExcTail {
+	UT       val[N > 0 ? N : 1];
+	uint16_t pos[N > 0 ? N : 1];
+};
+template <typename UT, int N>
+__device__ __forceinline__ ExcTail<UT, N> load_exception_tail(const ColView& col, const MetaRegs& m, int t) {
+	ExcTail<UT, N> x;
+	if constexpr (N > 0) {
+		const uint32_t  cnt = m.exc_cnt();
+		const UT*       ev  = static_cast<const UT*>(col.exc_val) + m.exc_off();
+		const uint16_t* ep  = col.exc_pos + m.exc_off();
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			const uint32_t i = (uint32_t)t + 32u * (k + 1);
+			x.val[k]         = 0;
+			x.pos[k]         = 0;
+			if (i < cnt && m.scheme() == ALPB200_SCHEME_ALP) {
+				x.val[k] = __ldg(ev + i);
+				x.pos[k] = __ldg(ep + i);
+			}
+		}
+	}
+	return x;
+}
 // exceptions 32.. of a vector: pull their cache lines towards the SM one vector ahead (lane i takes line i)
 __device__ __forceinline__ void prefetch_exception_tail(const ColView& col, const MetaRegs& m, int t, uint32_t value_bytes) {
 	const uint32_t cnt = m.exc_cnt();
@@ -208,17 +244,28 @@ __device__ __forceinline__ void prefetch_exception_tail(const ColView& col, cons
 }
 
 // ALP exception patch (decoder.hpp:141-149)
-template <typename PT>
+template <typename PT, int TAIL = 0>
 __device__ __forceinline__ void patch_alp(const ColView& col, const MetaRegs& m, const ExcRegs<typename Traits<PT>::UT>& x,
-                                          PT* __restrict__ out_vec, int t) {
+                                          PT* __restrict__ out_vec, int t,
+                                          const ExcTail<typename Traits<PT>::UT, TAIL>* tail = nullptr) {
 	using UT           = typename Traits<PT>::UT;
 	const uint32_t cnt = m.exc_cnt();
 	UT*            ov  = reinterpret_cast<UT*>(out_vec);
 	if ((uint32_t)t < cnt) { ov[x.pos] = x.val; }
-	if (cnt > 32) {
+	uint32_t from = 32;
+	if constexpr (TAIL > 0) {
+		if (tail != nullptr) {
+#pragma unroll
+			for (int k = 0; k < TAIL; k++) {
+				if ((uint32_t)t + 32u * (k + 1) < cnt) { ov[tail->pos[k]] = tail->val[k]; }
+			}
+			from = 32u * (TAIL + 1);
+		}
+	}
+	if (cnt > from) {
 		const UT*       ev = static_cast<const UT*>(col.exc_val) + m.exc_off();
 		const uint16_t* ep = col.exc_pos + m.exc_off();
-		for (uint32_t i = t + 32; i < cnt; i += 96) {  // three independent (position, value) loads in flight per lane
+		for (uint32_t i = t + from; i < cnt; i += 96) {  // three independent (position, value) loads in flight per lane
 			const uint32_t i1 = i + 32, i2 = i + 64;
 			uint32_t       p0 = ep[i], p1 = 0, p2 = 0;
 			UT             v0 = ev[i], v1 = 0, v2 = 0;
@@ -310,7 +357,7 @@ __device__ __forceinline__ void decode_rd_vector(const uint8_t* stage, const Col
 // DRAM sees dense sequential writes.  Without it (wide blocks, e.g. ALP_RD, where the tile would halve occupancy) the
 // warp stores full 128-byte lines directly and patches exceptions afterwards while the lines are still in L2.
 template <typename PT, int WARPS, bool OUT_TILE>
-__global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
+__global__ void __launch_bounds__(WARPS * 32, DecCfg<PT>::MINBLOCKS) decode_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
                                                                PT* __restrict__ out, uint32_t stage_bytes,
                                                                unsigned long long* __restrict__ counter,
                                                                const unsigned long long* __restrict__ oversize) {
@@ -374,14 +421,19 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 	MetaRegs nxt      = cur;
 	if (has_next) { nxt = load_meta(meta + v_next); }
 	issue(cur, 0);
+	constexpr int NTAIL = DecCfg<PT>::EXC_TAIL;
+	using XT            = ExcTail<UT, NTAIL>;
 	ExcRegs<UT> xcur  = load_exceptions<UT>(col, cur, t);
+	XT          tcur  = load_exception_tail<UT, NTAIL>(col, cur, t);
 	uint32_t    phase = 0;  // bit s: parity the next wait on stage s must see
 	for (int s = 0;; s ^= 1) {
 		ExcRegs<UT> xnxt = xcur;
+		XT          tnxt = tcur;
 		if (has_next) {
 			issue(nxt, s ^ 1);  // stage s^1 was drained one iteration ago (see __syncwarp below)
 			xnxt = load_exceptions<UT>(col, nxt, t);
-			prefetch_exception_tail(col, nxt, t, sizeof(UT));
+			tnxt = load_exception_tail<UT, NTAIL>(col, nxt, t);
+			if (NTAIL == 0 || nxt.exc_cnt() > 32u * (NTAIL + 1) || nxt.scheme() != ALPB200_SCHEME_ALP) { prefetch_exception_tail(col, nxt, t, sizeof(UT)); }
 		}
 		const uint64_t v_nn   = has_next ? take() : v_next;
 		const bool     has_nn = has_next && v_nn < n_vectors;
@@ -403,7 +455,7 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 		if (cur.scheme() == ALPB200_SCHEME_ALP) {
 			decode_alp_vector(stg, cur, out_vec, t);
 			__syncwarp();  // orders the patch stores after the lane-interleaved main stores
-			patch_alp<PT>(col, cur, xcur, out_vec, t);
+			patch_alp<PT, NTAIL>(col, cur, xcur, out_vec, t, &tcur);
 		} else {
 			decode_rd_vector<PT>(stg, col, cur, xcur, out_vec, t);
 		}
@@ -421,6 +473,7 @@ __global__ void __launch_bounds__(WARPS * 32, ALPB200_DEC_MINBLOCKS) decode_kern
 		cur      = nxt;
 		nxt      = nn;
 		xcur     = xnxt;
+		tcur     = tnxt;
 		has_next = has_nn;
 		v        = v_next;
 		v_next   = v_nn;

@@ -548,6 +548,9 @@ __device__ __forceinline__ void emit_exceptions(uint32_t myexc, int t, ValueOf&&
 #ifndef ALPB200_ENC_LOOKBACK
 #define ALPB200_ENC_LOOKBACK 1  // 1: blocks resolve their prefix by look-back from the scanner's anchors; 0: per-block prefixes from the scanner
 #endif
+#ifndef ALPB200_ENC_EARLY_ANCHOR
+#define ALPB200_ENC_EARLY_ANCHOR 1  // the look-back's anchor words are requested before the pack (one L2 round trip off the wait)
+#endif
 #ifndef ALPB200_ENC_SPIN_NS
 #define ALPB200_ENC_SPIN_NS 100  // back-off of the thread that polls for its block's prefix (frees issue slots and L2 bandwidth); 0 = none
 #endif
@@ -655,7 +658,10 @@ __device__ __forceinline__ void scan_blocks(const uint64_t* aggregates, uint64_t
 // (Round 1 tried a fixed 32-block window on top of per-block prefixes — the window's start still waited for the scanner —
 // and a 128-wide window re-read in full on every poll, ~1 TB/s of L2 traffic; both lost.  The adaptive anchor is what
 // takes the scanner off the critical path, the per-entry re-poll what keeps the traffic down.)
-constexpr uint32_t LB_GROUP = 32, LB_DEPTH = 8;
+#ifndef ALPB200_ENC_LB_DEPTH
+#define ALPB200_ENC_LB_DEPTH 4  // groups of 32 blocks a look-back reaches back (A/B on B200: 3-4 beat 8 by 1.5-4 %: the nearest anchor is 1-2 groups away)
+#endif
+constexpr uint32_t LB_GROUP = 32, LB_DEPTH = ALPB200_ENC_LB_DEPTH;
 
 // run by one warp: anchors[G + 1] = exclusive prefix of block 32 (G + 1), for every complete group of 32 blocks, in order
 // (anchors[0] = the call's start offset, written by encode_prepare_kernel)
@@ -685,15 +691,22 @@ __device__ __forceinline__ void scan_anchors(const uint64_t* aggregates, uint64_
 	}
 }
 
+// the anchor words a look-back starts from (lane j: anchor g - j).  They can be loaded ahead of time: a block issues this right
+// after publishing its aggregate and packs its vector while the words are on their way (ALPB200_ENC_EARLY_ANCHOR).
+__device__ __forceinline__ uint64_t lookback_anchor_word(const uint64_t* anchors, uint32_t bid, int t) {
+	const uint32_t g = bid / LB_GROUP;
+	return ((uint32_t)t < LB_DEPTH && (uint32_t)t <= g) ? ld_volatile_u64(&anchors[g - t]) : 0ull;
+}
 // run by one warp of a block that has published its aggregate: the exclusive prefix of block `bid`
-__device__ __forceinline__ uint64_t lookback_prefix(const uint64_t* aggregates, const uint64_t* anchors, uint32_t bid, int t) {
+__device__ __forceinline__ uint64_t lookback_prefix(const uint64_t* aggregates, const uint64_t* anchors, uint32_t bid, int t,
+                                                    uint64_t early_anchor = 0) {
 	const uint32_t g = bid / LB_GROUP;
 	// the nearest anchor that is already published, at most LB_DEPTH - 1 groups back (lane j looks at anchor g - j)
 	uint64_t base = 0;
 	uint32_t G    = 0;
-	for (;;) {
-		uint64_t a = 0;
-		if ((uint32_t)t < LB_DEPTH && (uint32_t)t <= g) { a = ld_volatile_u64(&anchors[g - t]); }
+	for (bool first = true;; first = false) {
+		uint64_t a = early_anchor;
+		if (!first || !__any_sync(FULL, (early_anchor & SCAN_VALID) != 0)) { a = lookback_anchor_word(anchors, bid, t); }
 		const uint32_t ok = __ballot_sync(FULL, (a & SCAN_VALID) != 0);
 		if (ok) {
 			const int j = __ffs((int)ok) - 1;
@@ -877,7 +890,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	__syncthreads();
 	uint64_t* aggregates = workspace + 2;
 	uint64_t* prefixes   = aggregates + gridDim.x;
-	uint64_t  agg        = 0, early_excl = 0;
+	uint64_t  agg        = 0, early_excl = 0, early_anchor = 0;
 	if (warp == 0) {
 		uint64_t mine_agg = 0;
 		if (t < WARPS) { mine_agg = ((uint64_t)s_units[t] << AGG_SHIFT) | s_cnt[t]; }
@@ -902,6 +915,9 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 			}
 			atomicMax(reinterpret_cast<unsigned long long*>(&col.totals[3]), (unsigned long long)wide * 128ull);
 		}
+#if ALPB200_ENC_LOOKBACK && ALPB200_ENC_EARLY_ANCHOR
+		if (ORDERED && bid != 0) { early_anchor = lookback_anchor_word(prefixes, bid, t); }  // consumed after the pack below
+#endif
 	}
 	const uint32_t bytes = units * 128u;
 	// ---- exceptions, first part: ranks, and the ORIGINALS of up to EXC_CAP exceptions into registers -------------------------
@@ -979,7 +995,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 			if (t == 0) { excl = workspace[1]; }  // where this call's output starts (0 unless appending)
 		} else {
 #if ALPB200_ENC_LOOKBACK
-			excl = lookback_prefix(aggregates, prefixes, bid, t);  // (`prefixes` holds the anchors in this scheme)
+			excl = lookback_prefix(aggregates, prefixes, bid, t, early_anchor);  // (`prefixes` holds the anchors in this scheme)
 #else
 			if (t == 0) {
 				while (!((excl = ld_volatile_u64(&prefixes[bid])) & SCAN_VALID)) { enc_backoff(); }
