@@ -12,6 +12,8 @@ from .codec import (  # noqa: F401
     HostCodec,
     decode,
     SUM_DECIMAL,
+    decode_minmax,
+    minmax_result,
     decode_sum,
     decode_values,
     device_count,
@@ -29,6 +31,8 @@ __all__ = [
     "LIB_PATH",
     "decode",
     "SUM_DECIMAL",
+    "decode_minmax",
+    "minmax_result",
     "decode_sum",
     "decode_values",
     "device_count",

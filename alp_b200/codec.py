@@ -251,6 +251,26 @@ def decode_sum(col, first=0, n=None, out=None, flags=0):
     return out
 
 
+def decode_minmax(col, first=0, n=None, out=None):
+    """Fused decode + MIN / MAX / COUNT of vectors [first, first+n): returns the 3-element float64 CUDA tensor `out`
+    (min, max, count-as-bits); use minmax_result() to read it.  NaNs are ignored; nothing is written back to HBM."""
+    n = col.n_vectors - first if n is None else n
+    if out is None:
+        out = torch.empty(3, dtype=torch.float64, device=col.device)
+    _require_cuda(out, "out")
+    st = col.as_struct()
+    with torch.cuda.device(col.device):
+        fn = getattr(lib, "alpb200_decode_minmax_" + _sfx(col.value_bytes))
+        check(fn(ctypes.byref(st), first, n, out.data_ptr(), _stream_ptr(col.device)))
+    return out
+
+
+def minmax_result(out):
+    """(min, max, count) from decode_minmax's tensor (synchronises)."""
+    h = out.cpu()
+    return float(h[0]), float(h[1]), int(h.view(torch.int64)[2])
+
+
 def generate(n_values, kind, device, seed=None, first_index=0, out=None):
     """Synthetic columns of SURVEY.md §8d on the device: kind 2 decimal f64, 3 high-precision f64, 4 mixed f32."""
     seed = {2: 42, 3: 43, 4: 44}[kind] if seed is None else seed

@@ -44,6 +44,8 @@ template <typename PT>
 int launch_decode(const alpb200_column* col, uint64_t first, uint64_t n, PT* d_out, void* stream);
 template <typename PT>
 int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream, uint32_t flags = 0);
+template <typename PT>
+int launch_decode_minmax(const alpb200_column* col, uint64_t first, uint64_t n, alpb200_minmax* d_out, void* stream);
 template <typename PT, bool ORDERED>
 int launch_encode_impl(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
                        bool append);

@@ -340,4 +340,308 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_sum_kernel(ColV
 	if (t == 0) { atomicAdd(sum, acc); }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Fused decode + MIN / MAX / COUNT (alpb200_decode_minmax_*): the scan-side siblings of SUM that an engine's zone maps and
+// filters ask for.  The reference ships no such scan (its scan query is alp_func + aggr_plus, q1.cpp:63-102); the semantics
+// are those of decode + reduce: MIN / MAX over the decoded values with NaNs ignored, COUNT = number of non-NaN values.
+// Nothing depends on what a writer left in exception slots: the exceptions' rows are marked in a per-warp bitmap (one atomicOr
+// per exception) and skipped by their owners, the exceptions' true values are taken from the exception arrays.
+// Nothing is written back to HBM: read-bound like SUM, the same pipeline (persistent warps, chunks, TMA stages).
+// ---------------------------------------------------------------------------------------------------------------------------
+struct MinMaxOut {  // = alpb200_minmax (include/alp_b200.h)
+	double             min, max;
+	unsigned long long count;
+};
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+	unsigned long long* a   = reinterpret_cast<unsigned long long*>(addr);
+	unsigned long long  old = *a;
+	while (v < __longlong_as_double((long long)old)) {
+		const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+		if (seen == old) { break; }
+		old = seen;
+	}
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+	unsigned long long* a   = reinterpret_cast<unsigned long long*>(addr);
+	unsigned long long  old = *a;
+	while (v > __longlong_as_double((long long)old)) {
+		const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+		if (seen == old) { break; }
+		old = seen;
+	}
+}
+static __global__ void minmax_init_kernel(MinMaxOut* out) {
+	out->min   = __longlong_as_double(0x7FF0000000000000ll);   // +inf
+	out->max   = __longlong_as_double((long long)0xFFF0000000000000ull);  // -inf
+	out->count = 0;
+}
+
+// One vector's MIN / MAX / COUNT into the thread's running (mn, mx, cnt).  `excrows`: bit r = the thread's row r is an exception
+// slot (skipped here; the exceptions' true values are added by the caller).
+// Decoding is monotonic in the encoded integer (multiplications by positive constants, round-to-nearest) as long as no integer
+// product wraps, so the thread takes the unsigned min / max of its FIELDS (2-4 instructions per value) and decodes just those
+// two with the reference's recipe — bit-identical to decoding all 32 and comparing.  Wrapping is judged on the two candidates
+// themselves (if neither base + field nor its product with 10^f wraps for the smallest and the largest integer, nothing in
+// between does); a vector with a candidate that might wrap — possible only in columns whose non-exception slots do not
+// round-trip — is decoded slot by slot instead.
+template <typename PT>
+__device__ __forceinline__ void minmax_alp_vector(const uint8_t* stage, const MetaRegs& m, int t, uint32_t excrows, double& mn, double& mx, uint32_t& cnt) {
+	using T            = Traits<PT>;
+	using UT           = typename T::UT;
+	using ST           = typename T::ST;
+	const uint32_t bw  = m.bw();
+	const uint32_t own = ~excrows;
+	cnt += __popc(own);  // a decoded ALP slot is never NaN
+	UT lo_f = (UT) ~(UT)0, hi_f = 0;
+	if constexpr (sizeof(PT) == 8) {
+		dispatch_width<0, 32>(bw > 32 ? 0u : bw, [&](auto W) {  // (wider fields: slot by slot below; their unpack windows cost too many registers)
+			constexpr int BW = decltype(W)::value;
+			uint32_t      a = 0xFFFFFFFFu, b = 0;
+			unpack64_rows<BW>(stage, t & 15, t >> 4, [&](int r, uint32_t lo, uint32_t) {
+				if ((own >> r) & 1u) {
+					a = min(a, lo);
+					b = max(b, lo);
+				}
+			});
+			lo_f = a;
+			hi_f = b;
+		});
+	} else {
+		dispatch_width<0, 32>(bw, [&](auto W) {
+			constexpr int BW = decltype(W)::value;
+			uint32_t      a = 0xFFFFFFFFu, b = 0;
+			unpack32_rows<BW>(stage, t, [&](int r, uint32_t d) {
+				if ((own >> r) & 1u) {
+					a = min(a, d);
+					b = max(b, d);
+				}
+			});
+			lo_f = a;
+			hi_f = b;
+		});
+	}
+	const UT base = sizeof(PT) == 8 ? (UT)m.base() : (UT)m.a.x;
+	const ST x_lo = (ST)(lo_f + base), x_hi = (ST)(hi_f + base), sbase = (ST)base;
+	bool     ok   = sizeof(PT) == 4 || bw <= 32;
+	if (own && ok) {
+		ok = x_lo >= sbase && x_hi >= x_lo;  // base + field did not leave the signed range
+		if constexpr (sizeof(PT) == 8) {
+			// |x| * 10^f < 2^63, exactly (128-bit product): config 2 has vectors whose largest non-exception sits 0.0001 % below the limit
+			const uint64_t f10 = (uint64_t)T::fact10(m.f());
+			const uint64_t alo = (uint64_t)(x_lo < 0 ? -x_lo : x_lo), ahi = (uint64_t)(x_hi < 0 ? -x_hi : x_hi);
+			ok = ok && __umul64hi(alo, f10) == 0 && (alo * f10) < (1ull << 63) && __umul64hi(ahi, f10) == 0 && (ahi * f10) < (1ull << 63);
+		} else {
+			const int64_t f10 = m.f() <= 9 ? Traits<double>::fact10(m.f()) : (1ll << 40);  // (float FACT[10] is the reference's 0: slot by slot)
+			const int64_t a = (int64_t)x_lo * f10, b = (int64_t)x_hi * f10;
+			ok = ok && a > -(1ll << 31) && a < (1ll << 31) && b > -(1ll << 31) && b < (1ll << 31);
+		}
+	}
+	if (__all_sync(FULL, ok)) {
+		if (own) {
+			const double dlo = (double)decode_value<PT>(x_lo, T::fact10(m.f()), T::frac10(m.e()));
+			const double dhi = (double)decode_value<PT>(x_hi, T::fact10(m.f()), T::frac10(m.e()));
+			mn               = dlo < mn ? dlo : mn;
+			mx               = dhi > mx ? dhi : mx;
+		}
+		return;
+	}
+	// rare: integer products that may wrap — every slot decoded with run-time extraction
+#pragma unroll 1
+	for (int r = 0; r < 32; r++) {
+		if ((own >> r) & 1u) {
+			const double x = alp_value_at(stage, m, (uint32_t)Map<PT>::index(t, r), PT());
+			mn             = x < mn ? x : mn;
+			mx             = x > mx ? x : mx;
+		}
+	}
+}
+// ALP_RD: any bit pattern can occur, so every slot is glued and compared.  Not inlined: the width-specialised unpack's window
+// (up to 63 words) gets its own register allocation instead of competing with the kernel's pipeline state.
+struct MinMaxAcc {
+	double   mn, mx;
+	uint32_t cnt;
+};
+template <typename PT>
+__device__ __noinline__ MinMaxAcc minmax_rd_vector(const uint8_t* stage, MetaRegs m, int t, uint32_t excrows, MinMaxAcc in) {
+	using UT   = typename Traits<PT>::UT;
+	double   a = in.mn, b = in.mx;
+	uint32_t c = 0;
+	rd_unpack_rows(stage, m, t, PT(), [&](int r, UT bits) {
+		const double x = (double)Traits<PT>::from_bits(bits);
+		if (!((excrows >> r) & 1u) && x == x) {
+			c++;
+			a = x < a ? x : a;
+			b = x > b ? x : b;
+		}
+	});
+	in.mn = a;
+	in.mx = b;
+	in.cnt += c;
+	return in;
+}
+
+template <typename PT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_minmax_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors,
+                                                                     MinMaxOut* __restrict__ result, uint32_t stage_bytes,
+                                                                     unsigned long long* __restrict__ counter,
+                                                                     const unsigned long long* __restrict__ oversize) {
+	using UT = typename Traits<PT>::UT;
+	constexpr int K = SumCfg<PT>::EXC_K;
+	using XR        = ExcRegsK<UT, K>;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint32_t s_rows[WARPS][32];  // per vector: bit r of word j = row r of thread j is an exception slot
+	const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	double    mn = __longlong_as_double(0x7FF0000000000000ll), mx = -mn;
+	uint32_t  cnt = 0;
+	const alpb200_vec_meta* meta = col.meta + first_vector;
+	auto take_value = [&](UT bits) {  // one true value (an exception's)
+		const double x = (double)Traits<PT>::from_bits(bits);
+		if (x == x) {
+			cnt++;
+			mn = x < mn ? x : mn;
+			mx = x > mx ? x : mx;
+		}
+	};
+	if (oversize != nullptr && *oversize != 0) {  // the hint was too small for this call (hint_check_kernel): slow, correct
+		const uint64_t n_warps = (uint64_t)gridDim.x * WARPS;
+		for (uint64_t w = (uint64_t)blockIdx.x * WARPS + warp; w < n_vectors; w += n_warps) {
+			const MetaRegs  m   = load_meta(meta + w);
+			const uint8_t*  blk = col.packed + (uint64_t)m.packed_off() * 128u;
+			const UT*       ev  = static_cast<const UT*>(col.exc_val) + m.exc_off();
+			const uint16_t* ep  = col.exc_pos + m.exc_off();
+			const bool      rd  = m.scheme() != ALPB200_SCHEME_ALP;
+			s_rows[warp][t]     = 0;
+			__syncwarp();
+			for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
+				const uint32_t p = ep[i];
+				atomicOr(&s_rows[warp][p & 31], 1u << (p >> 5));  // (slow path: value i belongs to lane i % 32, row i / 32)
+				UT v = ev[i];
+				if (rd) { v = (UT)(((v & 0xFFFFu) << m.bw()) | (value_bits_slow<PT>(blk, m, p) & low_mask<UT>((int)m.bw()))); }
+				take_value(v);
+			}
+			__syncwarp();
+			const uint32_t skip = s_rows[warp][t];
+#pragma unroll 1
+			for (int r = 0; r < 32; r++) {
+				if (!((skip >> r) & 1u)) { take_value(value_bits_slow<PT>(blk, m, (uint32_t)(32 * r + t))); }
+			}
+			__syncwarp();
+		}
+	} else {
+		uint8_t*  stage = smem + (size_t)warp * 2 * stage_bytes;
+		uint64_t* bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * 2 * stage_bytes) + 2 * warp;
+		if (t == 0) {
+			mbar_init(&bars[0], 1);
+			mbar_init(&bars[1], 1);
+			fence_mbar_init();
+		}
+		__syncwarp();
+		constexpr uint32_t CHUNK = 16, REFILL_AT = 6;
+		auto draw = [&]() -> uint64_t {
+			unsigned long long b = 0;
+			if (t == 0) { b = atomicAdd(counter, (unsigned long long)CHUNK); }
+			return shfl_u64(b, 0);
+		};
+		uint64_t chunk_base = draw(), next_base = 0;
+		uint32_t chunk_used = 0;
+		auto     take       = [&]() -> uint64_t {
+            if (chunk_used == CHUNK) {
+                chunk_base = next_base;
+                chunk_used = 0;
+            }
+            const uint64_t idx = chunk_base + chunk_used++;
+            if (chunk_used == CHUNK - REFILL_AT) { next_base = draw(); }
+            return idx;
+		};
+		uint64_t v = take(), v_next = take();
+		if (v < n_vectors) {
+			auto issue = [&](const MetaRegs& m, int s) {
+				const uint32_t bytes = m.block_bytes();
+				if (t == 0 && bytes != 0) {
+					mbar_arrive_expect_tx(&bars[s], bytes);
+					bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
+				}
+			};
+			MetaRegs cur      = load_meta(meta + v);
+			bool     has_next = v_next < n_vectors;
+			MetaRegs nxt      = cur;
+			if (has_next) { nxt = load_meta(meta + v_next); }
+			issue(cur, 0);
+			XR       xcur  = load_exceptions_k<UT, K>(col, cur, t);
+			uint32_t phase = 0;
+			for (int s = 0;; s ^= 1) {
+				XR xnxt = xcur;
+				if (has_next) {
+					issue(nxt, s ^ 1);
+					xnxt = load_exceptions_k<UT, K>(col, nxt, t);
+					if (nxt.exc_cnt() > 32u * K) { prefetch_exception_tail(col, nxt, t, sizeof(UT)); }
+				}
+				const uint64_t v_nn   = has_next ? take() : v_next;
+				const bool     has_nn = has_next && v_nn < n_vectors;
+				MetaRegs       nn     = nxt;
+				if (has_nn) { nn = load_meta(meta + v_nn); }
+				const uint8_t* stg = stage + (size_t)s * stage_bytes;
+				if (cur.block_bytes() != 0) {
+					mbar_wait(&bars[s], (phase >> s) & 1u);
+					phase ^= 1u << s;
+				}
+				const uint32_t  n_exc = cur.exc_cnt();
+				const UT*       ev    = static_cast<const UT*>(col.exc_val) + cur.exc_off();
+				const uint16_t* ep    = col.exc_pos + cur.exc_off();
+				const bool      rd    = cur.scheme() != ALPB200_SCHEME_ALP;
+				const uint32_t  rbw   = cur.bw();
+				// the exceptions: their rows are marked for the owners to skip, their true values are taken here
+				uint32_t excrows = 0;
+				if (n_exc != 0) {
+					s_rows[warp][t] = 0;
+					__syncwarp();
+					auto one = [&](uint32_t p, UT val) {
+						atomicOr(&s_rows[warp][Map<PT>::thread_of((int)p)], 1u << Map<PT>::row_of((int)p));
+						take_value(rd ? (UT)(((val & 0xFFFFu) << rbw) | rd_right_at(stg, rbw, p, UT())) : val);
+					};
+#pragma unroll
+					for (int k = 0; k < K; k++) {
+						if ((uint32_t)t + 32u * k < n_exc) { one(xcur.pos(k), xcur.val[k]); }
+					}
+					for (uint32_t i = (uint32_t)t + 32u * K; i < n_exc; i += 32) {
+						one(ep[i], ev[i]);
+					}
+					__syncwarp();
+					excrows = s_rows[warp][t];
+				}
+				if (!rd) {
+					minmax_alp_vector<PT>(stg, cur, t, excrows, mn, mx, cnt);
+				} else {
+					MinMaxAcc acc {mn, mx, cnt};
+					acc = minmax_rd_vector<PT>(stg, cur, t, excrows, acc);
+					mn  = acc.mn;
+					mx  = acc.mx;
+					cnt = acc.cnt;
+				}
+				__syncwarp();
+				if (!has_next) { break; }
+				cur      = nxt;
+				nxt      = nn;
+				xcur     = xnxt;
+				has_next = has_nn;
+				v        = v_next;
+				v_next   = v_nn;
+			}
+		}
+	}
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1) {
+		const double omn = __longlong_as_double((long long)shfl_xor_i64((int64_t)__double_as_longlong(mn), m));
+		const double omx = __longlong_as_double((long long)shfl_xor_i64((int64_t)__double_as_longlong(mx), m));
+		mn               = omn < mn ? omn : mn;
+		mx               = omx > mx ? omx : mx;
+	}
+	cnt = __reduce_add_sync(FULL, cnt);
+	if (t == 0 && cnt != 0) {
+		atomic_min_double(&result->min, mn);
+		atomic_max_double(&result->max, mx);
+		atomicAdd(&result->count, (unsigned long long)cnt);
+	}
+}
+
 }  // namespace alpb200

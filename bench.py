@@ -412,6 +412,13 @@ def config_block(kind, n, dev, rank, peak, steps, with_cpu, cpu_seconds):
     alp_b200.decode_sum(col, out=acc)
     want = float(x.sum(dtype=torch.float64).item())
     got = float(acc.item())
+    mm = torch.empty(3, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        alp_b200.decode_minmax(col, out=mm)
+    mm_ms = cuda_ms(lambda: alp_b200.decode_minmax(col, out=mm), steps)
+    mm_min, mm_max, mm_cnt = alp_b200.minmax_result(mm)
+    mm_ok = mm_min == float(x.min().item()) and mm_max == float(x.max().item()) and mm_cnt == int((x == x).sum().item())
+    assert mm_ok, "config %d: fused MIN / MAX / COUNT differs from torch's over the original column" % kind
     dec_block = None
     if vb == 4:  # float columns: the decimal-sum variant (integers added exactly, one conversion per thread; include/alp_b200.h)
         for _ in range(3):
@@ -449,6 +456,9 @@ def config_block(kind, n, dev, rank, peak, steps, with_cpu, cpu_seconds):
         "scan_sum": {"ms": scan_ms, "GBps_decoded_equivalent": rate(scan_ms, n * vb), "read_GBps": rate(scan_ms, read_bytes),
                      "roofline_frac": rate(scan_ms, read_bytes) / peak, "rel_err_vs_torch_sum": abs(got - want) / max(abs(want), 1e-300)},
     }
+    block["scan_minmax"] = {"ms": mm_ms, "GBps_decoded_equivalent": rate(mm_ms, n * vb), "read_GBps": rate(mm_ms, read_bytes),
+                            "roofline_frac": rate(mm_ms, read_bytes) / peak, "matches_torch_min_max_count": bool(mm_ok),
+                            "api": "alpb200_decode_minmax_* (decode + patch in shared memory, reduce; nothing written back)"}
     if dec_block is not None:
         block["scan_sum_decimal"] = dec_block
     if with_cpu:

@@ -247,6 +247,21 @@ int alpb200_decode_sum_ex_f64(const alpb200_column* col, uint64_t first_vector, 
 int alpb200_decode_sum_ex_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, double* d_sum, uint32_t flags,
                               void* stream);
 
+/* Fused decode + MIN / MAX / COUNT (no decoded column is written): the scan-side siblings of SUM (zone maps, filters).
+ * *d_out (device memory, overwritten) receives the minimum and maximum of the decoded values of vectors [first_vector,
+ * first_vector + n_vectors) as doubles, NaNs ignored, and the number of non-NaN values; an empty range or an all-NaN range
+ * gives min = +inf, max = -inf, count = 0.  Semantics = decode + reduce (the reference ships no such scan; its scan query is
+ * SUM only, q1.cpp:63-102): every vector is decoded and patched like alpb200_decode_* does, in shared memory. */
+typedef struct alpb200_minmax {
+	double   min;
+	double   max;
+	uint64_t count;
+} alpb200_minmax;
+int alpb200_decode_minmax_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, alpb200_minmax* d_out,
+                              void* stream);
+int alpb200_decode_minmax_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, alpb200_minmax* d_out,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host engine calls; copies are part of the call).
  * A codec context owns device staging buffers, a small pinned area and three streams so that repeated

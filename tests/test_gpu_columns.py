@@ -654,6 +654,49 @@ def test_decimal_sum_of_a_float_column(checker):
     assert abs(a - b) <= 1e-12 * abs(a)
 
 
+def test_fused_decode_minmax_count(checker):
+    """alpb200_decode_minmax_*: MIN / MAX / COUNT over the decoded values, NaNs ignored — against numpy over the CHECKER's decoded
+    column, for ALP, ALP_RD and float columns, exception-heavy vectors, NaN / Inf / -0.0, sub-ranges and the empty range."""
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    rng = np.random.default_rng(21)
+    specials = np.round(rng.normal(0, 1000, 1024 * 7), 2)
+    specials[rng.integers(0, specials.size, 300)] = np.nan
+    specials[5], specials[6000], specials[77] = np.inf, -np.inf, -0.0
+    cols = {
+        "config2": pyoracle.generate(2 * 102400 + 5 * 1024, 2),
+        "config3_rd": pyoracle.generate(102400 + 9 * 1024, 3),
+        "config4_f32": pyoracle.generate(102400 + 3 * 1024, 4),
+        "negatives": (rng.integers(-10**7, 10**7, size=1024 * 33) / 1000.0),
+        "specials": specials,
+        "all_nan": np.full(2048, np.nan),
+        "random_bits": rng.integers(0, 1 << 63, size=1024 * 11, dtype=np.uint64).view(np.float64),
+    }
+    for name, x in cols.items():
+        col = alp_b200.encode(torch.from_numpy(x).to(_dev()))
+        col.read_totals()
+        decoded = checker.decode_column(col.to_host()).astype(np.float64)
+        for first, n in ((0, col.n_vectors), (1, max(0, col.n_vectors - 2)), (0, 0)):
+            part = decoded[first * 1024 : (first + n) * 1024]
+            valid = part[~np.isnan(part)]
+            mn, mx, cnt = alp_b200.minmax_result(alp_b200.decode_minmax(col, first, n))
+            assert cnt == valid.size, (name, first, n, cnt, valid.size)
+            if valid.size:
+                assert mn == valid.min() and mx == valid.max(), (name, first, n, mn, mx, valid.min(), valid.max())
+            else:
+                assert mn == np.inf and mx == -np.inf, (name, mn, mx)
+    # a stale block-size hint takes the slow path and gives the same answer
+    x = pyoracle.generate(102400, 3)
+    col = alp_b200.encode(torch.from_numpy(x).to(_dev()))
+    col.read_totals()
+    col.max_block_bytes = 1024
+    mn, mx, cnt = alp_b200.minmax_result(alp_b200.decode_minmax(col))
+    assert (mn, mx, cnt) == (float(x.min()), float(x.max()), x.size)
+
+
 def test_fused_decode_sum_propagates_nan():
     import torch
 

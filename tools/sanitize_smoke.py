@@ -35,6 +35,7 @@ for x in cols:
         assert torch.equal(x.view(ib), y.view(ib))
         s = alp_b200.decode_sum(col)
         s = alp_b200.decode_sum(col, flags=alp_b200.SUM_DECIMAL)
+        alp_b200.minmax_result(alp_b200.decode_minmax(col))
         torch.cuda.synchronize()
 from alp_b200 import primitives as gpu  # noqa: E402
 
