@@ -12,6 +12,7 @@ from .codec import (  # noqa: F401
     HostCodec,
     decode,
     SUM_DECIMAL,
+    decode_filter,
     decode_minmax,
     minmax_result,
     decode_sum,
@@ -31,6 +32,7 @@ __all__ = [
     "LIB_PATH",
     "decode",
     "SUM_DECIMAL",
+    "decode_filter",
     "decode_minmax",
     "minmax_result",
     "decode_sum",

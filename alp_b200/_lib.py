@@ -53,6 +53,8 @@ SIGNATURES = {
     "alpb200_decode_sum_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_minmax_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
     "alpb200_decode_minmax_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _P], _c.c_int),
+    "alpb200_decode_filter_f64": ([_P, _c.c_uint64, _c.c_uint64, _c.c_uint32, _c.c_double, _P, _P, _P], _c.c_int),
+    "alpb200_decode_filter_f32": ([_P, _c.c_uint64, _c.c_uint64, _c.c_uint32, _c.c_double, _P, _P, _P], _c.c_int),
     "alpb200_decode_sum_ex_f64": ([_P, _c.c_uint64, _c.c_uint64, _P, _c.c_uint32, _P], _c.c_int),
     "alpb200_decode_sum_ex_f32": ([_P, _c.c_uint64, _c.c_uint64, _P, _c.c_uint32, _P], _c.c_int),
     "alpb200_ctx_create": ([_P, _c.c_int, _c.c_uint64, _c.c_int], _c.c_int),

@@ -265,6 +265,26 @@ def decode_minmax(col, first=0, n=None, out=None):
     return out
 
 
+FILTER_OPS = {"<": 0, "<=": 1, ">": 2, ">=": 3, "==": 4, "!=": 5}  # ALPB200_FILTER_*
+
+
+def decode_filter(col, op, constant, first=0, n=None, bitmap=None, selected=None):
+    """Fused decode + predicate filter of vectors [first, first+n): returns (bitmap, selected) — an int32 CUDA tensor of
+    32 words per vector (bit j of word w of a vector = its value 32 w + j satisfies `value op constant`) and a 1-element
+    int64 CUDA tensor with the number of set bits.  op: one of FILTER_OPS' keys."""
+    n = col.n_vectors - first if n is None else n
+    if bitmap is None:
+        bitmap = torch.empty(32 * n, dtype=torch.int32, device=col.device)
+    if selected is None:
+        selected = torch.zeros(1, dtype=torch.int64, device=col.device)
+    _require_cuda(bitmap, "bitmap")
+    st = col.as_struct()
+    with torch.cuda.device(col.device):
+        fn = getattr(lib, "alpb200_decode_filter_" + _sfx(col.value_bytes))
+        check(fn(ctypes.byref(st), first, n, FILTER_OPS[op], float(constant), bitmap.data_ptr(), selected.data_ptr(), _stream_ptr(col.device)))
+    return bitmap, selected
+
+
 def minmax_result(out):
     """(min, max, count) from decode_minmax's tensor (synchronises)."""
     h = out.cpu()

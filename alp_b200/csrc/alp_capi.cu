@@ -534,6 +534,14 @@ int alpb200_decode_minmax_f64(const alpb200_column* col, uint64_t first, uint64_
 int alpb200_decode_minmax_f32(const alpb200_column* col, uint64_t first, uint64_t n, alpb200_minmax* d_out, void* stream) {
 	return launch_decode_minmax<float>(col, first, n, d_out, stream);
 }
+int alpb200_decode_filter_f64(const alpb200_column* col, uint64_t first, uint64_t n, uint32_t op, double constant, uint32_t* d_bitmap,
+                              uint64_t* d_selected, void* stream) {
+	return launch_decode_filter<double>(col, first, n, op, constant, d_bitmap, d_selected, stream);
+}
+int alpb200_decode_filter_f32(const alpb200_column* col, uint64_t first, uint64_t n, uint32_t op, double constant, uint32_t* d_bitmap,
+                              uint64_t* d_selected, void* stream) {
+	return launch_decode_filter<float>(col, first, n, op, constant, d_bitmap, d_selected, stream);
+}
 int alpb200_decode_sum_ex_f64(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, uint32_t flags, void* stream) {
 	if (flags & ~(uint32_t)ALPB200_SUM_DECIMAL) { return fail(ALPB200_EINVAL, "decode_sum_ex: unknown flag"); }
 	return launch_decode_sum<double>(col, first, n, d_sum, stream, flags);

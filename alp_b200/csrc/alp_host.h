@@ -46,6 +46,9 @@ template <typename PT>
 int launch_decode_sum(const alpb200_column* col, uint64_t first, uint64_t n, double* d_sum, void* stream, uint32_t flags = 0);
 template <typename PT>
 int launch_decode_minmax(const alpb200_column* col, uint64_t first, uint64_t n, alpb200_minmax* d_out, void* stream);
+template <typename PT>
+int launch_decode_filter(const alpb200_column* col, uint64_t first, uint64_t n, uint32_t op, double constant, uint32_t* d_bitmap,
+                         uint64_t* d_selected, void* stream);
 template <typename PT, bool ORDERED>
 int launch_encode_impl(const PT* d_in, uint64_t n, const alpb200_rg_state* d_states, const alpb200_column* col, void* ws, void* stream,
                        bool append);

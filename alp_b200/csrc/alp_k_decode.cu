@@ -152,6 +152,50 @@ int launch_decode_minmax(const alpb200_column* col, uint64_t first, uint64_t n, 
 template int launch_decode_minmax<double>(const alpb200_column*, uint64_t, uint64_t, alpb200_minmax*, void*);
 template int launch_decode_minmax<float>(const alpb200_column*, uint64_t, uint64_t, alpb200_minmax*, void*);
 
+template <typename PT>
+int launch_decode_filter(const alpb200_column* col, uint64_t first, uint64_t n, uint32_t op, double constant, uint32_t* d_bitmap,
+                         uint64_t* d_selected, void* stream) {
+	if (!col || !d_bitmap) { return fail(ALPB200_EINVAL, "decode_filter: null argument"); }
+	if (op > ALPB200_FILTER_NE) { return fail(ALPB200_EINVAL, "decode_filter: unknown comparison"); }
+	if (first + n > col->n_vectors) { return fail(ALPB200_EINVAL, "decode_filter: vector range outside the column"); }
+	if ((reinterpret_cast<uintptr_t>(d_bitmap) & 3u) != 0 || (reinterpret_cast<uintptr_t>(d_selected) & 7u) != 0) {
+		return fail(ALPB200_EINVAL, "decode_filter: misaligned output");
+	}
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	if (d_selected) { CUDA_TRY(cudaMemsetAsync(d_selected, 0, sizeof(uint64_t), s)); }
+	if (n == 0) { return ALPB200_OK; }
+	if (!col->meta || !col->packed) { return fail(ALPB200_EINVAL, "decode_filter: null argument"); }
+	if ((reinterpret_cast<uintptr_t>(col->packed) & 127u) != 0) { return fail(ALPB200_EINVAL, "decode_filter: column.packed must be 128-byte aligned"); }
+	if ((reinterpret_cast<uintptr_t>(col->meta) & 15u) != 0) { return fail(ALPB200_EINVAL, "decode_filter: column.meta must be 16-byte aligned"); }
+	DeviceInfo di;
+	if (int rc = device_info(di)) { return rc; }
+	const uint32_t widest = (sizeof(PT) == 8 ? 66u : 35u) * 128u;
+	uint32_t       block  = col->max_block_bytes ? (uint32_t)std::min<uint64_t>(col->max_block_bytes, widest) : widest;
+	const uint32_t stage  = ((block + 127u) & ~127u) + STAGE_PAD;
+	constexpr int  W      = 8;
+	const size_t   smem   = (size_t)W * (VEC * sizeof(PT) + 2 * stage) + W * 2 * sizeof(uint64_t);
+	auto           kern   = decode_filter_kernel<PT, W>;
+	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem));
+	if (per_sm < 1) { return fail(ALPB200_ECUDA, "decode_filter: kernel does not fit on an SM"); }
+	unsigned long long* counter  = di.counters + di.next_counter;
+	unsigned long long* oversize = nullptr;
+	CUDA_TRY(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long), s));
+	if (block < widest) {  // a hint was given: make sure it covers this call's blocks (see hint_check_kernel)
+		oversize = counter + 1;
+		hint_check_kernel<<<(uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)di.sms * 8), 256, 0, s>>>(col->meta + first, n, stage - STAGE_PAD, oversize);
+		CUDA_TRY(cudaGetLastError());
+	}
+	ColView        view {col->meta, col->packed, col->exc_val, col->exc_pos};
+	const uint32_t grid = (uint32_t)std::min<uint64_t>((n + W - 1) / W, (uint64_t)di.sms * per_sm);
+	kern<<<grid, W * 32, smem, s>>>(view, first, n, op, constant, d_bitmap, reinterpret_cast<unsigned long long*>(d_selected), stage, counter, oversize);
+	CUDA_TRY(cudaGetLastError());
+	return ALPB200_OK;
+}
+template int launch_decode_filter<double>(const alpb200_column*, uint64_t, uint64_t, uint32_t, double, uint32_t*, uint64_t*, void*);
+template int launch_decode_filter<float>(const alpb200_column*, uint64_t, uint64_t, uint32_t, double, uint32_t*, uint64_t*, void*);
+
 int validate_device(const alpb200_column* col, int value_bytes, uint64_t* h_max_block_bytes, void* stream) {
 	if (!col || (value_bytes != 8 && value_bytes != 4)) { return fail(ALPB200_EINVAL, "column_validate_device: bad argument"); }
 	if (h_max_block_bytes) { *h_max_block_bytes = 0; }

@@ -644,4 +644,117 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_minmax_kernel(C
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Fused decode + predicate filter (alpb200_decode_filter_*): a selection bitmap instead of the decoded column — 1 bit per value
+// out (128 bytes per vector) instead of 8 / 4 bytes.  Semantics = decode + compare: the vector is decoded and patched in a
+// per-warp shared-memory tile exactly like decode_kernel does (same device functions), every lane then compares values
+// 32 r + t and the warp's ballots are the bitmap words (bit j of word w of a vector = value 32 w + j); IEEE comparisons, i.e. a
+// NaN satisfies only NE.  The reference ships no filter scan (its scan query is SUM, q1.cpp:63-102).
+// ---------------------------------------------------------------------------------------------------------------------------
+// which of (less, equal, greater, unordered) satisfy the comparison: bits 0..3
+__device__ __forceinline__ uint32_t filter_mask(uint32_t op) {
+	switch (op) {
+	case ALPB200_FILTER_LT: return 1u;
+	case ALPB200_FILTER_LE: return 3u;
+	case ALPB200_FILTER_GT: return 4u;
+	case ALPB200_FILTER_GE: return 6u;
+	case ALPB200_FILTER_EQ: return 2u;
+	default: return 13u;  // NE: less, greater or unordered (NaN)
+	}
+}
+__device__ __forceinline__ bool filter_test(double x, double c, uint32_t mask) {  // branch-free: the comparison is a per-launch constant
+	const bool lt = x < c, eq = x == c, gt = x > c;
+	return ((mask & 1u) && lt) || ((mask & 2u) && eq) || ((mask & 4u) && gt) || ((mask & 8u) && !(lt || eq || gt));
+}
+template <typename PT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) decode_filter_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors, uint32_t op, double constant,
+                                                                     uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ selected,
+                                                                     uint32_t stage_bytes, unsigned long long* __restrict__ counter,
+                                                                     const unsigned long long* __restrict__ oversize) {
+	using UT = typename Traits<PT>::UT;
+	extern __shared__ __align__(128) uint8_t smem[];
+	const int          warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	constexpr uint32_t TILE = VEC * sizeof(PT);
+	uint8_t*           mine  = smem + (size_t)warp * (TILE + 2 * stage_bytes);
+	PT*                tile  = reinterpret_cast<PT*>(mine);
+	uint8_t*           stage = mine + TILE;
+	uint64_t*          bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * (TILE + 2 * stage_bytes)) + 2 * warp;
+	uint32_t           hits  = 0;
+	const uint32_t     fmask = filter_mask(op);
+	auto emit = [&](uint64_t v) {  // the patched vector sits in the tile: 32 ballots -> 32 words, one 128-byte store
+		__syncwarp();
+		uint32_t word = 0;
+#pragma unroll 8
+		for (int r = 0; r < 32; r++) {
+			const uint32_t b = __ballot_sync(FULL, filter_test((double)tile[32 * r + t], constant, fmask));
+			if (t == r) { word = b; }
+		}
+		bitmap[v * 32 + t] = word;
+		hits += __popc(word);
+		__syncwarp();
+	};
+	const alpb200_vec_meta* meta = col.meta + first_vector;
+	if (oversize != nullptr && *oversize != 0) {  // the hint was too small for this call (hint_check_kernel): slow, correct
+		const uint64_t n_warps = (uint64_t)gridDim.x * WARPS;
+		for (uint64_t w = (uint64_t)blockIdx.x * WARPS + warp; w < n_vectors; w += n_warps) {
+			decode_vector_slow<PT>(col, load_meta(meta + w), tile, t);
+			emit(w);
+		}
+	} else {
+		if (t == 0) {
+			mbar_init(&bars[0], 1);
+			mbar_init(&bars[1], 1);
+			fence_mbar_init();
+		}
+		__syncwarp();
+		constexpr uint32_t CHUNK = 16;
+		auto issue = [&](const MetaRegs& m, int s) {
+			const uint32_t bytes = m.block_bytes();
+			if (t == 0 && bytes != 0) {
+				mbar_arrive_expect_tx(&bars[s], bytes);
+				bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
+			}
+		};
+		uint32_t phase = 0;
+		for (;;) {  // chunks of 16 consecutive vectors from a global counter; inside a chunk the next block and its exceptions are in flight
+			unsigned long long b = 0;
+			if (t == 0) { b = atomicAdd(counter, (unsigned long long)CHUNK); }
+			const uint64_t base = shfl_u64(b, 0);
+			if (base >= n_vectors) { break; }
+			const uint32_t n   = (uint32_t)min((uint64_t)CHUNK, n_vectors - base);
+			MetaRegs       cur = load_meta(meta + base);
+			issue(cur, 0);
+			ExcRegs<UT> xcur = load_exceptions<UT>(col, cur, t);
+			for (uint32_t i = 0; i < n; i++) {
+				const int   s    = (int)(i & 1);
+				MetaRegs    nxt  = cur;
+				ExcRegs<UT> xnxt = xcur;
+				if (i + 1 < n) {
+					nxt = load_meta(meta + base + i + 1);
+					issue(nxt, s ^ 1);
+					xnxt = load_exceptions<UT>(col, nxt, t);
+					prefetch_exception_tail(col, nxt, t, sizeof(UT));
+				}
+				if (cur.block_bytes() != 0) {
+					mbar_wait(&bars[s], (phase >> s) & 1u);
+					phase ^= 1u << s;
+				}
+				const uint8_t* stg = stage + (size_t)s * stage_bytes;
+				if (cur.scheme() == ALPB200_SCHEME_ALP) {
+					decode_alp_vector(stg, cur, tile, t);
+					__syncwarp();  // orders the patch stores after the lane-interleaved main stores
+					patch_alp<PT>(col, cur, xcur, tile, t);
+				} else {
+					decode_rd_vector<PT>(stg, col, cur, xcur, tile, t);
+				}
+				emit(base + i);  // (its trailing __syncwarp also protects stage s before lane 0 refills it)
+				cur  = nxt;
+				xcur = xnxt;
+			}
+		}
+	}
+	hits = __reduce_add_sync(FULL, hits);
+	if (t == 0 && hits != 0 && selected != nullptr) { atomicAdd(selected, (unsigned long long)hits); }
+}
+
 }  // namespace alpb200

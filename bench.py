@@ -419,6 +419,17 @@ def config_block(kind, n, dev, rank, peak, steps, with_cpu, cpu_seconds):
     mm_min, mm_max, mm_cnt = alp_b200.minmax_result(mm)
     mm_ok = mm_min == float(x.min().item()) and mm_max == float(x.max().item()) and mm_cnt == int((x == x).sum().item())
     assert mm_ok, "config %d: fused MIN / MAX / COUNT differs from torch's over the original column" % kind
+    # predicate filter: `value < c` with c = the mean of MIN and MAX (selects a good share of every config's values)
+    f_c = 0.5 * (mm_min + mm_max)
+    f_bitmap = torch.empty(32 * (n // 1024), dtype=torch.int32, device=dev)
+    f_sel = torch.zeros(1, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        alp_b200.decode_filter(col, "<", f_c, bitmap=f_bitmap, selected=f_sel)
+    f_ms = cuda_ms(lambda: alp_b200.decode_filter(col, "<", f_c, bitmap=f_bitmap, selected=f_sel), steps)
+    f_want = int((x.double() < f_c).sum().item())
+    f_ok = int(f_sel.item()) == f_want
+    assert f_ok, "config %d: fused filter selected %d values, torch %d" % (kind, int(f_sel.item()), f_want)
+    del f_bitmap
     dec_block = None
     if vb == 4:  # float columns: the decimal-sum variant (integers added exactly, one conversion per thread; include/alp_b200.h)
         for _ in range(3):
@@ -459,6 +470,10 @@ def config_block(kind, n, dev, rank, peak, steps, with_cpu, cpu_seconds):
     block["scan_minmax"] = {"ms": mm_ms, "GBps_decoded_equivalent": rate(mm_ms, n * vb), "read_GBps": rate(mm_ms, read_bytes),
                             "roofline_frac": rate(mm_ms, read_bytes) / peak, "matches_torch_min_max_count": bool(mm_ok),
                             "api": "alpb200_decode_minmax_* (decode + patch in shared memory, reduce; nothing written back)"}
+    block["scan_filter"] = {"ms": f_ms, "GBps_decoded_equivalent": rate(f_ms, n * vb), "read_GBps": rate(f_ms, read_bytes),
+                            "roofline_frac": rate(f_ms, read_bytes + n // 8) / peak, "selected_fraction": f_want / n,
+                            "count_matches_torch": bool(f_ok),
+                            "api": "alpb200_decode_filter_* (value < constant -> 1 bit per value; decode + patch in shared memory)"}
     if dec_block is not None:
         block["scan_sum_decimal"] = dec_block
     if with_cpu:

@@ -262,6 +262,22 @@ int alpb200_decode_minmax_f64(const alpb200_column* col, uint64_t first_vector, 
 int alpb200_decode_minmax_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, alpb200_minmax* d_out,
                               void* stream);
 
+/* Fused decode + predicate filter: a selection bitmap instead of the decoded column.  Bit j of d_bitmap[32 v + w] (v counted
+ * from first_vector) is set iff value 32 w + j of vector first_vector + v satisfies `value op constant` (IEEE comparison in
+ * double: a NaN satisfies only ALPB200_FILTER_NE; float columns compare (double)value).  d_bitmap: 32 * n_vectors words
+ * (128 bytes per vector), 4-byte aligned; *d_selected (device memory, may be NULL, overwritten) receives the number of set
+ * bits.  Semantics = decode + compare: every vector is decoded and patched in shared memory like alpb200_decode_* does. */
+#define ALPB200_FILTER_LT 0u
+#define ALPB200_FILTER_LE 1u
+#define ALPB200_FILTER_GT 2u
+#define ALPB200_FILTER_GE 3u
+#define ALPB200_FILTER_EQ 4u
+#define ALPB200_FILTER_NE 5u
+int alpb200_decode_filter_f64(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, uint32_t op, double constant,
+                              uint32_t* d_bitmap, uint64_t* d_selected, void* stream);
+int alpb200_decode_filter_f32(const alpb200_column* col, uint64_t first_vector, uint64_t n_vectors, uint32_t op, double constant,
+                              uint32_t* d_bitmap, uint64_t* d_selected, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host engine calls; copies are part of the call).
  * A codec context owns device staging buffers, a small pinned area and three streams so that repeated
@@ -357,7 +373,10 @@ int alpb200_prim_rd_decode_f64(double* h_out, const uint64_t* h_right, const uin
 int alpb200_prim_rd_decode_f32(float* h_out, const uint32_t* h_right, const uint16_t* h_left, const uint16_t* h_exc,
                                const uint16_t* h_pos, uint16_t cnt, const alpb200_rg_state* h_state);
 /* alp::encoder<PT>::init (+ rd_encoder<PT>::init when the row-group falls to ALP_RD) on a host column:
- * the values [offset, min(offset+102400, n_values)) form the row-group. */
+ * the values [offset, min(offset+102400, n_values)) form the row-group.  Whole vectors only: a partial last vector is not
+ * sampled (the reference's sampler takes it when it is the row-group's first vector or holds at least 32 values,
+ * sampler.hpp:30-47) and a row-group without one complete vector is ALPB200_EINVAL — pad the tail first
+ * (alpb200_fill_invalid_*), as the batched path does. */
 int alpb200_prim_init_f64(const double* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
 int alpb200_prim_init_f32(const float* h_col, uint64_t offset, uint64_t n_values, alpb200_rg_state* h_state);
 /* alp::rd_encoder<PT>::init (rd.hpp:180-185) on its own: the row-group is made an ALP_RD row-group whatever the ALP search

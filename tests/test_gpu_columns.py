@@ -697,6 +697,42 @@ def test_fused_decode_minmax_count(checker):
     assert (mn, mx, cnt) == (float(x.min()), float(x.max()), x.size)
 
 
+@pytest.mark.parametrize("op", ["<", "<=", ">", ">=", "==", "!="])
+def test_fused_decode_filter(op, checker):
+    """alpb200_decode_filter_*: the selection bitmap of `value op constant` against numpy over the CHECKER's decoded column
+    (ALP, ALP_RD, floats, exception-heavy vectors, NaN / Inf), bit for bit, with the count of selected values."""
+    import operator
+
+    import torch
+
+    import alp_b200
+    from oracle import pyoracle
+
+    fn = {"<": operator.lt, "<=": operator.le, ">": operator.gt, ">=": operator.ge, "==": operator.eq, "!=": operator.ne}[op]
+    rng = np.random.default_rng(31)
+    specials = np.round(rng.normal(0, 1000, 1024 * 7), 2)
+    specials[rng.integers(0, specials.size, 300)] = np.nan
+    specials[5], specials[6000] = np.inf, -np.inf
+    cols = {
+        "config2": (pyoracle.generate(102400 + 5 * 1024, 2), 123.4),
+        "config3_rd": (pyoracle.generate(102400 + 9 * 1024, 3), None),
+        "config4_f32": (pyoracle.generate(102400 + 3 * 1024, 4), None),
+        "specials": (specials, 0.0),
+    }
+    for name, (x, c) in cols.items():
+        if c is None:
+            c = float(np.nanmedian(x.astype(np.float64)))  # a value of the column itself: == / != have something to find
+        col = alp_b200.encode(torch.from_numpy(x).to(_dev()))
+        col.read_totals()
+        decoded = checker.decode_column(col.to_host()).astype(np.float64)
+        for first, n in ((0, col.n_vectors), (2, col.n_vectors - 3)):
+            bitmap, selected = alp_b200.decode_filter(col, op, c, first, n)
+            want = fn(decoded[first * 1024 : (first + n) * 1024], c)
+            got = np.unpackbits(bitmap.cpu().numpy().view(np.uint8), bitorder="little").astype(bool)
+            assert got.shape == want.shape and np.array_equal(got, want), (name, op, first, n, int(got.sum()), int(want.sum()))
+            assert int(selected.item()) == int(want.sum()), (name, op)
+
+
 def test_fused_decode_sum_propagates_nan():
     import torch
 

@@ -36,6 +36,7 @@ for x in cols:
         s = alp_b200.decode_sum(col)
         s = alp_b200.decode_sum(col, flags=alp_b200.SUM_DECIMAL)
         alp_b200.minmax_result(alp_b200.decode_minmax(col))
+        alp_b200.decode_filter(col, "<=", 10.0)
         torch.cuda.synchronize()
 from alp_b200 import primitives as gpu  # noqa: E402
 
