@@ -173,7 +173,7 @@ int launch_decode_filter(const alpb200_column* col, uint64_t first, uint64_t n, 
 	uint32_t       block  = col->max_block_bytes ? (uint32_t)std::min<uint64_t>(col->max_block_bytes, widest) : widest;
 	const uint32_t stage  = ((block + 127u) & ~127u) + STAGE_PAD;
 	constexpr int  W      = 8;
-	const size_t   smem   = (size_t)W * (VEC * sizeof(PT) + 2 * stage) + W * 2 * sizeof(uint64_t);
+	const size_t   smem   = (size_t)W * 2 * stage + W * 2 * sizeof(uint64_t);
 	auto           kern   = decode_filter_kernel<PT, W>;
 	CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;

@@ -646,11 +646,15 @@ __global__ void __launch_bounds__(WARPS * 32, 32 / WARPS) decode_minmax_kernel(C
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // Fused decode + predicate filter (alpb200_decode_filter_*): a selection bitmap instead of the decoded column — 1 bit per value
-// out (128 bytes per vector) instead of 8 / 4 bytes.  Semantics = decode + compare: the vector is decoded and patched in a
-// per-warp shared-memory tile exactly like decode_kernel does (same device functions), every lane then compares values
-// 32 r + t and the warp's ballots are the bitmap words (bit j of word w of a vector = value 32 w + j); IEEE comparisons, i.e. a
-// NaN satisfies only NE.  The reference ships no filter scan (its scan query is SUM, q1.cpp:63-102).
+// out (128 bytes per vector) instead of 8 / 4 bytes.  Semantics = decode + compare, exact by construction: every slot is decoded
+// with the reference's recipe IN REGISTERS (no tile: 32 resident warps like SUM) and compared, the warp's ballots are the bitmap
+// words (bit j of word w of a vector = value 32 w + j), and the exceptions' bits are then corrected from their true values in a
+// 128-byte shared-memory copy of the words; IEEE comparisons, i.e. a NaN satisfies only NE.  The reference ships no filter scan
+// (its scan query is SUM, q1.cpp:63-102).
 // ---------------------------------------------------------------------------------------------------------------------------
+#ifndef ALPB200_FILTER_BLOCKS
+#define ALPB200_FILTER_BLOCKS 3  // resident 8-warp blocks per SM the register allocation is limited for
+#endif
 // which of (less, equal, greater, unordered) satisfy the comparison: bits 0..3
 __device__ __forceinline__ uint32_t filter_mask(uint32_t op) {
 	switch (op) {
@@ -666,90 +670,208 @@ __device__ __forceinline__ bool filter_test(double x, double c, uint32_t mask) {
 	const bool lt = x < c, eq = x == c, gt = x > c;
 	return ((mask & 1u) && lt) || ((mask & 2u) && eq) || ((mask & 4u) && gt) || ((mask & 8u) && !(lt || eq || gt));
 }
-template <typename PT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) decode_filter_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors, uint32_t op, double constant,
-                                                                     uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ selected,
-                                                                     uint32_t stage_bytes, unsigned long long* __restrict__ counter,
-                                                                     const unsigned long long* __restrict__ oversize) {
-	using UT = typename Traits<PT>::UT;
-	extern __shared__ __align__(128) uint8_t smem[];
-	const int          warp = threadIdx.x >> 5, t = threadIdx.x & 31;
-	constexpr uint32_t TILE = VEC * sizeof(PT);
-	uint8_t*           mine  = smem + (size_t)warp * (TILE + 2 * stage_bytes);
-	PT*                tile  = reinterpret_cast<PT*>(mine);
-	uint8_t*           stage = mine + TILE;
-	uint64_t*          bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * (TILE + 2 * stage_bytes)) + 2 * warp;
-	uint32_t           hits  = 0;
-	const uint32_t     fmask = filter_mask(op);
-	auto emit = [&](uint64_t v) {  // the patched vector sits in the tile: 32 ballots -> 32 words, one 128-byte store
-		__syncwarp();
-		uint32_t word = 0;
-#pragma unroll 8
-		for (int r = 0; r < 32; r++) {
-			const uint32_t b = __ballot_sync(FULL, filter_test((double)tile[32 * r + t], constant, fmask));
-			if (t == r) { word = b; }
+// per-thread results -> bitmap words.  A thread collects the outcomes of its 32 rows in one register (bit r = row r; no warp-wide
+// step per row), a 32x32 bit-matrix transpose (transpose32, alp_encode.cuh: 5 shuffle rounds) turns that into "lane r holds the
+// ballot of row r", and the layout does the rest: a thread's row r is value Map<PT>::index(t, r) — floats 32 r + t, so the ballot
+// of row r IS word r; doubles 512 half + 16 r + lane, so the low / high halves of the ballots of rows 2 w and 2 w + 1 make words w
+// and 16 + w (two shuffles).  Lane w ends up holding word w.
+template <typename PT>
+struct BitWords {
+	uint32_t mask = 0;
+	__device__ __forceinline__ void row(int r, bool pass, int) { mask |= (uint32_t)pass << r; }
+	__device__ __forceinline__ uint32_t words(int t) const {
+		const uint32_t x = transpose32(mask, t);
+		if constexpr (sizeof(PT) == 4) {
+			return x;
+		} else {
+			const uint32_t a = __shfl_sync(FULL, x, 2 * (t & 15)), b = __shfl_sync(FULL, x, 2 * (t & 15) + 1);
+			return t < 16 ? ((a & 0xFFFFu) | (b << 16)) : ((a >> 16) | (b & 0xFFFF0000u));
 		}
-		bitmap[v * 32 + t] = word;
-		hits += __popc(word);
-		__syncwarp();
-	};
+	}
+};
+// ALP_RD vectors (inlined: at the filter kernel's 80 registers a call costs more than the window's spills, 4.2 vs 2.3 ms per 2^30
+// values of config 3 — the opposite of the MIN / MAX kernel at 64 registers)
+template <typename PT>
+__device__ __forceinline__ uint32_t filter_rd_vector(const uint8_t* stage, MetaRegs m, int t, double constant, uint32_t fmask) {
+	using UT = typename Traits<PT>::UT;
+	BitWords<PT> w;
+	rd_unpack_rows(stage, m, t, PT(), [&](int r, UT bits) { w.row(r, filter_test((double)Traits<PT>::from_bits(bits), constant, fmask), t); });
+	return w.words(t);
+}
+
+template <typename PT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, ALPB200_FILTER_BLOCKS) decode_filter_kernel(ColView col, uint64_t first_vector, uint64_t n_vectors, uint32_t op,
+                                                                     double constant, uint32_t* __restrict__ bitmap,
+                                                                     unsigned long long* __restrict__ selected, uint32_t stage_bytes,
+                                                                     unsigned long long* __restrict__ counter,
+                                                                     const unsigned long long* __restrict__ oversize) {
+	using T  = Traits<PT>;
+	using UT = typename T::UT;
+	using ST = typename T::ST;
+	constexpr int K = SumCfg<PT>::EXC_K;
+	using XR        = ExcRegsK<UT, K>;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint32_t s_bits[WARPS][32];  // a vector's bitmap words while its exceptions' bits are corrected
+	const int      warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	const uint32_t fmask = filter_mask(op);
+	uint32_t       hits  = 0;
 	const alpb200_vec_meta* meta = col.meta + first_vector;
 	if (oversize != nullptr && *oversize != 0) {  // the hint was too small for this call (hint_check_kernel): slow, correct
 		const uint64_t n_warps = (uint64_t)gridDim.x * WARPS;
 		for (uint64_t w = (uint64_t)blockIdx.x * WARPS + warp; w < n_vectors; w += n_warps) {
-			decode_vector_slow<PT>(col, load_meta(meta + w), tile, t);
-			emit(w);
+			const MetaRegs  m   = load_meta(meta + w);
+			const uint8_t*  blk = col.packed + (uint64_t)m.packed_off() * 128u;
+			const UT*       ev  = static_cast<const UT*>(col.exc_val) + m.exc_off();
+			const uint16_t* ep  = col.exc_pos + m.exc_off();
+			const bool      rd  = m.scheme() != ALPB200_SCHEME_ALP;
+			uint32_t        word = 0;
+#pragma unroll 1
+			for (int r = 0; r < 32; r++) {  // (here value 32 r + t belongs to lane t, row r — for doubles too)
+				const uint32_t b = __ballot_sync(FULL, filter_test((double)T::from_bits(value_bits_slow<PT>(blk, m, (uint32_t)(32 * r + t))), constant, fmask));
+				if (t == r) { word = b; }
+			}
+			s_bits[warp][t] = word;
+			__syncwarp();
+			for (uint32_t i = t; i < m.exc_cnt(); i += 32) {
+				const uint32_t p = ep[i];
+				UT             v = ev[i];
+				if (rd) { v = (UT)(((v & 0xFFFFu) << m.bw()) | (value_bits_slow<PT>(blk, m, p) & low_mask<UT>((int)m.bw()))); }
+				atomicAnd(&s_bits[warp][p >> 5], ~(1u << (p & 31)));
+				if (filter_test((double)T::from_bits(v), constant, fmask)) { atomicOr(&s_bits[warp][p >> 5], 1u << (p & 31)); }
+			}
+			__syncwarp();
+			word               = s_bits[warp][t];
+			bitmap[w * 32 + t] = word;
+			hits += __popc(word);
+			__syncwarp();
 		}
 	} else {
+		uint8_t*  stage = smem + (size_t)warp * 2 * stage_bytes;
+		uint64_t* bars  = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * 2 * stage_bytes) + 2 * warp;
 		if (t == 0) {
 			mbar_init(&bars[0], 1);
 			mbar_init(&bars[1], 1);
 			fence_mbar_init();
 		}
 		__syncwarp();
-		constexpr uint32_t CHUNK = 16;
-		auto issue = [&](const MetaRegs& m, int s) {
-			const uint32_t bytes = m.block_bytes();
-			if (t == 0 && bytes != 0) {
-				mbar_arrive_expect_tx(&bars[s], bytes);
-				bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
-			}
-		};
-		uint32_t phase = 0;
-		for (;;) {  // chunks of 16 consecutive vectors from a global counter; inside a chunk the next block and its exceptions are in flight
+		constexpr uint32_t CHUNK = 16, REFILL_AT = 6;
+		auto draw = [&]() -> uint64_t {
 			unsigned long long b = 0;
 			if (t == 0) { b = atomicAdd(counter, (unsigned long long)CHUNK); }
-			const uint64_t base = shfl_u64(b, 0);
-			if (base >= n_vectors) { break; }
-			const uint32_t n   = (uint32_t)min((uint64_t)CHUNK, n_vectors - base);
-			MetaRegs       cur = load_meta(meta + base);
-			issue(cur, 0);
-			ExcRegs<UT> xcur = load_exceptions<UT>(col, cur, t);
-			for (uint32_t i = 0; i < n; i++) {
-				const int   s    = (int)(i & 1);
-				MetaRegs    nxt  = cur;
-				ExcRegs<UT> xnxt = xcur;
-				if (i + 1 < n) {
-					nxt = load_meta(meta + base + i + 1);
-					issue(nxt, s ^ 1);
-					xnxt = load_exceptions<UT>(col, nxt, t);
-					prefetch_exception_tail(col, nxt, t, sizeof(UT));
+			return shfl_u64(b, 0);
+		};
+		uint64_t chunk_base = draw(), next_base = 0;
+		uint32_t chunk_used = 0;
+		auto     take       = [&]() -> uint64_t {
+            if (chunk_used == CHUNK) {
+                chunk_base = next_base;
+                chunk_used = 0;
+            }
+            const uint64_t idx = chunk_base + chunk_used++;
+            if (chunk_used == CHUNK - REFILL_AT) { next_base = draw(); }
+            return idx;
+		};
+		uint64_t v = take(), v_next = take();
+		if (v < n_vectors) {
+			auto issue = [&](const MetaRegs& m, int s) {
+				const uint32_t bytes = m.block_bytes();
+				if (t == 0 && bytes != 0) {
+					mbar_arrive_expect_tx(&bars[s], bytes);
+					bulk_g2s(stage + (size_t)s * stage_bytes, col.packed + (uint64_t)m.packed_off() * 128u, bytes, &bars[s]);
 				}
+			};
+			MetaRegs cur      = load_meta(meta + v);
+			bool     has_next = v_next < n_vectors;
+			MetaRegs nxt      = cur;
+			if (has_next) { nxt = load_meta(meta + v_next); }
+			issue(cur, 0);
+			XR       xcur  = load_exceptions_k<UT, K>(col, cur, t);
+			uint32_t phase = 0;
+			for (int s = 0;; s ^= 1) {
+				XR xnxt = xcur;
+				if (has_next) {
+					issue(nxt, s ^ 1);
+					xnxt = load_exceptions_k<UT, K>(col, nxt, t);
+					if (nxt.exc_cnt() > 32u * K) { prefetch_exception_tail(col, nxt, t, sizeof(UT)); }
+				}
+				const uint64_t v_nn   = has_next ? take() : v_next;
+				const bool     has_nn = has_next && v_nn < n_vectors;
+				MetaRegs       nn     = nxt;
+				if (has_nn) { nn = load_meta(meta + v_nn); }
+				const uint8_t* stg = stage + (size_t)s * stage_bytes;
 				if (cur.block_bytes() != 0) {
 					mbar_wait(&bars[s], (phase >> s) & 1u);
 					phase ^= 1u << s;
 				}
-				const uint8_t* stg = stage + (size_t)s * stage_bytes;
-				if (cur.scheme() == ALPB200_SCHEME_ALP) {
-					decode_alp_vector(stg, cur, tile, t);
-					__syncwarp();  // orders the patch stores after the lane-interleaved main stores
-					patch_alp<PT>(col, cur, xcur, tile, t);
+				const uint32_t  n_exc = cur.exc_cnt();
+				const UT*       ev    = static_cast<const UT*>(col.exc_val) + cur.exc_off();
+				const uint16_t* ep    = col.exc_pos + cur.exc_off();
+				const bool      rd    = cur.scheme() != ALPB200_SCHEME_ALP;
+				const uint32_t  rbw   = cur.bw();
+				uint32_t        word;
+				if (rd) {
+					word = filter_rd_vector<PT>(stg, cur, t, constant, fmask);
 				} else {
-					decode_rd_vector<PT>(stg, col, cur, xcur, tile, t);
+					// every slot decoded with the reference's recipe in registers and compared: exact by construction
+					const ST bw_ok = (ST)0;
+					(void)bw_ok;
+					const auto fact = T::fact10(cur.f());
+					const auto frac = T::frac10(cur.e());
+					BitWords<PT> w;
+					if constexpr (sizeof(PT) == 8) {
+						const uint64_t base = cur.base();
+						if (cur.bw() <= 32) {
+							dispatch_width<0, 32>(cur.bw(), [&](auto Wc) {
+								constexpr int BW = decltype(Wc)::value;
+								unpack64_rows<BW>(stg, t & 15, t >> 4, [&](int r, uint32_t lo, uint32_t) {
+									w.row(r, filter_test(decode_value<double>((int64_t)((uint64_t)lo + base), fact, frac), constant, fmask), t);
+								});
+							});
+						} else {  // wide fields (rare): run-time extraction
+#pragma unroll 1
+							for (int r = 0; r < 32; r++) {
+								w.row(r, filter_test(alp_value_at(stg, cur, (uint32_t)Map<PT>::index(t, r), PT()), constant, fmask), t);
+							}
+						}
+					} else {
+						const uint32_t base = cur.a.x;
+						dispatch_width<0, 32>(cur.bw(), [&](auto Wc) {
+							constexpr int BW = decltype(Wc)::value;
+							unpack32_rows<BW>(stg, t, [&](int r, uint32_t d) {
+								w.row(r, filter_test((double)decode_value<float>((int32_t)(d + base), fact, frac), constant, fmask), t);
+							});
+						});
+					}
+					word = w.words(t);
 				}
-				emit(base + i);  // (its trailing __syncwarp also protects stage s before lane 0 refills it)
-				cur  = nxt;
-				xcur = xnxt;
+				if (n_exc != 0) {  // the exceptions' bits, from their true values
+					s_bits[warp][t] = word;
+					__syncwarp();
+					auto one = [&](uint32_t p, UT val) {
+						const UT bits = rd ? (UT)(((val & 0xFFFFu) << rbw) | rd_right_at(stg, rbw, p, UT())) : val;
+						atomicAnd(&s_bits[warp][p >> 5], ~(1u << (p & 31)));
+						if (filter_test((double)T::from_bits(bits), constant, fmask)) { atomicOr(&s_bits[warp][p >> 5], 1u << (p & 31)); }
+					};
+#pragma unroll
+					for (int k = 0; k < K; k++) {
+						if ((uint32_t)t + 32u * k < n_exc) { one(xcur.pos(k), xcur.val[k]); }
+					}
+					for (uint32_t i = (uint32_t)t + 32u * K; i < n_exc; i += 32) {
+						one(ep[i], ev[i]);
+					}
+					__syncwarp();
+					word = s_bits[warp][t];
+				}
+				bitmap[v * 32 + t] = word;
+				hits += __popc(word);
+				__syncwarp();  // stage s and s_bits are free again
+				if (!has_next) { break; }
+				cur      = nxt;
+				nxt      = nn;
+				xcur     = xnxt;
+				has_next = has_nn;
+				v        = v_next;
+				v_next   = v_nn;
 			}
 		}
 	}
