@@ -610,6 +610,11 @@ def test_fused_decode_sum(kind):
     want = float(alp_b200.decode(col).double().sum().item())
     got = float(alp_b200.decode_sum(col).item())
     assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (kind, got, want)
+    # and against a sum made on the checker's side, from the checker's own decode of the column
+    from oracle import pyoracle
+
+    decoded = pyoracle.best().decode_column(col.to_host()).astype(np.float64)
+    assert abs(got - float(np.sum(decoded))) <= 1e-12 * float(np.sum(np.abs(decoded))), (kind, got, float(np.sum(decoded)))
     part = float(alp_b200.decode_sum(col, first=100, n=237).item())
     want_part = float(xd[100 * 1024 : 337 * 1024].double().sum().item())
     assert abs(part - want_part) <= 1e-9 * max(1.0, abs(want_part))
