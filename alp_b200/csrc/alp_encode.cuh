@@ -785,6 +785,15 @@ struct ColOut {
 //                  the same blocks, the same records (offsets differ), dense, but not sorted by vector.
 //
 // vectors (= warps) per thread block: build knobs (tools/build_variant.sh)
+// ALPB200_ENC_HELPER: the vector-order kernel's blocks carry one extra warp WITHOUT a vector.  It sums the block's sizes,
+// publishes the aggregate and resolves the block's prefix while the other warps pack — the look-back's L2 round trips leave the
+// path of the warps that hold tiles (with the work on warp 0, its pack and its look-back were in series: ~2 us of a ~10 us round).
+#ifndef ALPB200_ENC_HELPER
+#define ALPB200_ENC_HELPER 0
+#endif
+#ifndef ALPB200_ENC_WPS64
+#define ALPB200_ENC_WPS64 27  // resident warps per SM the f64 kernels' registers are limited for
+#endif
 #ifndef ALPB200_ENC_WARPS64
 #define ALPB200_ENC_WARPS64 9
 #endif
@@ -807,7 +816,7 @@ struct EncodeCfg<double> {
 	// Measured against 8 x 3 (80 registers): 2-3 % faster.
 	static constexpr int      EXC_REGS      = ALPB200_ENC_EXC_REGS64;  // exceptions held in registers per lane across the placement wait (x 32 per vector)
 	static constexpr int      WARPS         = ALPB200_ENC_WARPS64;
-	static constexpr int      WARPS_PER_SM  = 27 / WARPS * WARPS;
+	static constexpr int      WARPS_PER_SM  = ALPB200_ENC_WPS64;
 };
 template <>
 struct EncodeCfg<float> {
@@ -815,7 +824,7 @@ struct EncodeCfg<float> {
 	static constexpr uint32_t INPLACE_MAX   = SMEM_PER_WARP;
 	static constexpr int      EXC_REGS      = ALPB200_ENC_EXC_REGS32;
 	static constexpr int      WARPS         = ALPB200_ENC_WARPS32;
-	static constexpr int      WARPS_PER_SM  = 32 / WARPS * WARPS;  // 4.4 KiB and 64 registers
+	static constexpr int      WARPS_PER_SM  = 32;  // 4.4 KiB and 64 registers
 };
 
 // runs after the workspace was zeroed: appending calls continue at the column's running totals
@@ -825,8 +834,12 @@ static __global__ void encode_prepare_kernel(uint64_t* workspace, const uint64_t
 	workspace[2 + n_blocks] = SCAN_VALID | start;  // anchors[0] (look-back placement; the slot is prefixes[0] otherwise and rewritten)
 }
 
+template <bool ORDERED>
+__host__ __device__ constexpr int enc_helper_warps() {
+	return ORDERED && ALPB200_ENC_HELPER ? 1 : 0;
+}
 template <typename PT, int WARPS, bool ORDERED>
-__global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARPS) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
+__global__ void __launch_bounds__((WARPS + enc_helper_warps<ORDERED>()) * 32, EncodeCfg<PT>::WARPS_PER_SM / (WARPS + enc_helper_warps<ORDERED>())) encode_kernel(const PT* __restrict__ in, uint64_t n_vectors,
                                                                                     const alpb200_rg_state* __restrict__ states,
                                                                                     ColOut col, uint64_t* workspace) {
 	using T   = Traits<PT>;
@@ -849,8 +862,10 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		__syncthreads();
 		bid = s_bid;
 	}
+	constexpr int  PUB    = enc_helper_warps<ORDERED>() ? WARPS : 0;  // the warp that publishes the block's sizes and resolves its prefix
+	const bool     helper = enc_helper_warps<ORDERED>() && warp == WARPS;
 	const uint64_t v      = (uint64_t)bid * WARPS + warp;
-	const bool     active = v < n_vectors;
+	const bool     active = !helper && v < n_vectors;
 	uint8_t*       mine   = smem + (size_t)warp * Cfg::SMEM_PER_WARP;  // the tile
 	UT*            tile   = reinterpret_cast<UT*>(mine);
 
@@ -883,7 +898,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		}
 		units = rd ? a.bw + a.e : a.bw;
 	}
-	if (t == 0) {
+	if (t == 0 && !helper) {
 		s_units[warp] = units;
 		s_cnt[warp]   = a.cnt;
 	}
@@ -891,7 +906,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 	uint64_t* aggregates = workspace + 2;
 	uint64_t* prefixes   = aggregates + gridDim.x;
 	uint64_t  agg        = 0, early_excl = 0, early_anchor = 0;
-	if (warp == 0) {
+	if (warp == PUB) {
 		uint64_t mine_agg = 0;
 		if (t < WARPS) { mine_agg = ((uint64_t)s_units[t] << AGG_SHIFT) | s_cnt[t]; }
 		agg                 = warp_sum_u64(mine_agg);
@@ -987,7 +1002,7 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 			__syncwarp();
 		}
 	}
-	if (warp == 0) {
+	if (warp == PUB) {
 		uint64_t excl = 0;
 		if constexpr (!ORDERED) {
 			excl = early_excl;
@@ -1013,7 +1028,8 @@ __global__ void __launch_bounds__(WARPS * 32, EncodeCfg<PT>::WARPS_PER_SM / WARP
 		}
 	}
 	__syncthreads();
-	const bool scanner = ORDERED && bid == 0 && warp == WARPS - 1;  // this warp produces every block's prefix once its own work is done
+	// this warp produces every block's prefix once its own work is done (the helper warp when there is one)
+	const bool scanner = ORDERED && bid == 0 && warp == (enc_helper_warps<ORDERED>() ? WARPS : WARPS - 1);
 	if (!active) {
 		if (scanner) { run_scanner(aggregates, prefixes, gridDim.x, t, workspace[1]); }
 		return;
