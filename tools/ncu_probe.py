@@ -2,7 +2,7 @@
 """Run ONE hot-path launch a few times, for profiling under ncu (never a bench value).
 
     ncu --set full --import-source on --clock-control none -k regex:encode_kernel -s 1 -c 1 -o gpurun_out/enc \
-        python tools/ncu_probe.py encode 2 27          # what (encode|encode_unordered|decode|sum|minmax), column kind (2|3|4|int), log2(values)
+        python tools/ncu_probe.py encode 2 27          # what (encode|encode_unordered|decode|sum|minmax|filter), column kind (2|3|4|int), log2(values)
 """
 import os
 import sys
@@ -44,6 +44,8 @@ def main():
             alp_b200.decode_sum(col, out=acc)
         if what == "minmax":
             alp_b200.decode_minmax(col)
+        if what == "filter":
+            alp_b200.decode_filter(col, "<", 500.0)
     torch.cuda.synchronize()
 
 
